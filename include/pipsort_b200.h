@@ -1,0 +1,158 @@
+/* pipsort_b200 -- C-ABI of the B200 (sm_100a) posterior-calculation engine.
+ *
+ * This is the drop-in boundary for PIPSORT's PostCal hot path.  Every entry
+ * point cites the reference interface it replaces (paths relative to the PIPSORT source tree).
+ * Plain C types only; no torch, no C++ types.  All functions return 0 on success and a non-zero
+ * PIPSORT_E_* code on failure; pipsort_last_error() returns a human-readable message for the last
+ * failure on the calling thread.  The engine is single-caller (like PostCal, which is driven from
+ * the main thread after omp_set_num_threads(1), pipsort.cpp:222) and never retains host pointers:
+ * inputs are copied to the device in pipsort_create, outputs are written into caller-owned buffers.
+ *
+ * There is NO CPU fallback: every compute entry point fails with PIPSORT_E_CUDA when no CUDA device
+ * is usable.
+ */
+#ifndef PIPSORT_B200_H
+#define PIPSORT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIPSORT_OK 0
+#define PIPSORT_E_ARG 1      /* bad argument (message says which)                                  */
+#define PIPSORT_E_CUDA 2     /* CUDA runtime failure / no device                                   */
+#define PIPSORT_E_STUDIES 3  /* number of studies != 2 (postcal.cpp:20-23 exits for > 2)           */
+#define PIPSORT_E_RANGE 4    /* rank space / exponent range overflow                               */
+#define PIPSORT_E_SINGULAR 5 /* a causal sub-block lost positive definiteness (postcal.cpp:291-294) */
+
+#define PIPSORT_KMAX 8       /* max union SNPs per configuration on the scoring path               */
+#define PIPSORT_JMAX_EXH 3   /* exhaustive path: union subsets of size <= 3 (postcal.cpp:760-762)  */
+
+/* pipsort_create flags */
+#define PIPSORT_KEEP_ORDER 1u /* keep the snp_map order internally (default: union SNPs are relabelled
+                                 by type so that warps run one code path; sums are order independent) */
+
+typedef struct pipsort_engine pipsort_engine;
+
+/* Locus description = the PostCal constructor arguments the likelihood actually consumes
+ * (postcal.h:118-195).  The caller (Model, model.h:171-264) has already applied the PSD fix and the
+ * eigen-decomposition; what crosses the boundary is, per study s,
+ *   sigma_s = B_s^T B_s  (the effective LD; B = |Omega|^(1/2) Q^T is PostCal's BIG_SIGMA block), n_s x n_s,
+ *             row-major (symmetric, so arma's column-major is the same bytes), studies concatenated;
+ *   z_s     = B_s^T S'_s (S' is PostCal's S_LONG_VEC), n_s doubles, studies concatenated;
+ *   d_s     = s_squared * n_s / min(n) + t_squared   (postcal.cpp:66,89; only the diagonal of sigmaC
+ *             reaches the likelihood, postcal.cpp:250);
+ *   K       = S'^T S'  (postcal.cpp:285-287 with an empty causal set);
+ *   snp_map = PostCal::idx_to_snp_map, int32[S][U], study index of union SNP g or -1 (model.h:132).
+ */
+typedef struct pipsort_locus {
+    int32_t num_studies;       /* S, must be 2                                                     */
+    const int32_t* num_snps;   /* [S]      PostCal::num_snps_all                                   */
+    const double* sigma;       /* [sum n_s^2]                                                      */
+    const double* z;           /* [sum n_s]                                                        */
+    const double* d;           /* [S]                                                              */
+    double K;
+    int32_t union_count;       /* U        PostCal::unionSnpCount                                  */
+    const int32_t* snp_map;    /* [S*U]                                                            */
+    double gamma;              /* PostCal::gamma                                                   */
+    double sharing_param;      /* PostCal::sharing_param (p)                                       */
+    int32_t max_causal;        /* PostCal::maxCausalSNP (c); sizes the exponent range              */
+} pipsort_locus;
+
+/* Caller-owned output block = PostCal's result members (postcal.h:62-99), all in log space with 0.0
+ * meaning "nothing accumulated" exactly as addlogSpace leaves them (postcal.h:102-112).           */
+typedef struct pipsort_outputs {
+    double* total;        /* [1]   totalLikeLihoodLOG / sss_sum_lkl                                 */
+    double* postValues;   /* [N]   N = sum n_s, indexed offset_s + i  (postcal.cpp:1020-1030)        */
+    double* noCausal;     /* [S]   (postcal.cpp:988-1000)                                           */
+    double* sharedPips;   /* [U]   (postcal.cpp:1003-1012)                                          */
+    double* sharedLL;     /* [U]                                                                    */
+    double* notSharedLL;  /* [U]   (postcal.cpp:1014-1016)                                          */
+} pipsort_outputs;
+
+/* Replaces the PostCal constructor (postcal.h:118-195): copies the locus to `device` (CUDA ordinal),
+ * builds the device-side tables and zeroes the accumulators.                                       */
+int pipsort_create(const pipsort_locus* locus, int device, uint32_t flags, pipsort_engine** out);
+
+/* Replaces PostCal::~PostCal (postcal.h:197-204). */
+void pipsort_destroy(pipsort_engine* e);
+
+/* Zero the accumulators (a fresh PostCal has all-zero result arrays, postcal.h:129-160). */
+int pipsort_reset(pipsort_engine* e);
+
+/* Number of union subsets of size 0..c = the reference's total_iteration (postcal.cpp:723-725). */
+int pipsort_total_ranks(const pipsort_engine* e, int c, uint64_t* out);
+
+/* Replaces PostCal::computeTotalLikelihood (postcal.cpp:716-1092) restricted to the union-subset
+ * ranks [rank_begin, rank_end) in the reference's size-then-lexicographic order (nextBinary /
+ * findConfig, postcal.cpp:307-387) over the engine's SNP order (= the snp_map order when the engine
+ * was created with PIPSORT_KEEP_ORDER; a fixed relabelling of it otherwise, so a partition of
+ * [0,total) always reproduces the whole run).  Accumulates into the engine's device accumulators
+ * (asynchronously on the engine's stream); n_configs (optional) receives the number of expanded
+ * configurations evaluated so far after a stream sync.                                            */
+int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64_t rank_end);
+
+/* Replaces the body of the OpenMP loop of sss_computeTotalLikelihood, i.e. a batch of
+ * expand_and_compute_lkl calls (sss_postcal.cpp:223-255, 447-685): idx is int32[n][kmax] of union
+ * indices in snp_map order, -1 padded; make_updates (uint8[n], NULL = all 1) says which
+ * configurations are added to the accumulators; out_max_abs_l[n] receives the expansion value with
+ * the largest |l| (sss_postcal.cpp:560,624-626; 0.0 when no expansion exists).  Host buffers.       */
+int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n, int kmax,
+                                const uint8_t* make_updates, double* out_max_abs_l);
+
+/* Same with device-resident idx / make_updates / out buffers (no host copies, asynchronous). */
+int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
+                                       const uint8_t* d_make_updates, double* d_out_max_abs_l);
+
+/* Reads the accumulators into PostCal's result arrays (any member of `out` may be NULL).  Replaces the
+ * reads of totalLikeLihoodLOG / postValues / noCausal / sharedPips / sharedLL / notSharedLL by
+ * findOptimalSetGreedy (postcal.cpp:1144-1163) and printPost2File (postcal.h:288-336).            */
+int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out);
+
+/* Number of expanded configurations accumulated since the last reset (the reference's mycount). */
+int pipsort_config_count(pipsort_engine* e, uint64_t* out);
+
+/* Debug / parity: the configuration the reference evaluates at union-subset rank `rank`, expansion
+ * number `expansion` (ascending bmask order with checkOR rejects skipped, postcal.cpp:903-958), in
+ * snp_map order regardless of the engine's internal relabelling.  out_union_idx[c] gets the chosen
+ * union SNPs (ascending, -1 padded), out_state[c] 1 = study 0 only, 2 = study 1 only, 3 = both;
+ * *n_expansions the number of accepted expansions of that subset.  Evaluated on the device.        */
+int pipsort_enumerate(pipsort_engine* e, int c, uint64_t rank, uint32_t expansion, int32_t* out_union_idx,
+                      int32_t* out_state, uint32_t* n_expansions);
+
+/* Multi-GPU: the accumulators are one flat device array of doubles whose element-wise SUM over
+ * engines working on disjoint rank ranges of the same locus is the accumulator state of the union
+ * (SURVEY.md section 8e).  One process per GPU combines them with a single NCCL all-reduce(sum) on
+ * this buffer; a single process driving several devices can use pipsort_merge.                    */
+int pipsort_accumulator_buffer(pipsort_engine* e, void** device_ptr, uint64_t* num_doubles);
+int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copies across devices)  */
+
+/* Split [0,total) into `parts` contiguous rank ranges of roughly equal work (expanded configurations
+ * weighted); bounds receives parts+1 values.                                                      */
+int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds);
+
+/* Stream the engine works on (cudaStream_t as void*), and a blocking sync on it. */
+void* pipsort_stream(pipsort_engine* e);
+int pipsort_sync(pipsort_engine* e);
+
+/* Device-side timing of the launches issued between begin and end (CUDA events on the engine's
+ * stream): milliseconds.                                                                          */
+int pipsort_timer_begin(pipsort_engine* e);
+int pipsort_timer_end(pipsort_engine* e, float* ms);
+
+/* Number of engine kernels launched since create (bench.py's gpu_launches). */
+uint64_t pipsort_launch_count(const pipsort_engine* e);
+
+/* FP64 DFMA micro-benchmark (register-resident FMA chains on every SM): measured FLOP/s of `device`.
+ * Used as the roofline denominator (MEASURED_PEAKS.json carries no FP64 figure).                   */
+int pipsort_measure_fp64_peak(int device, double* flops_per_sec);
+
+const char* pipsort_last_error(void);
+const char* pipsort_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIPSORT_B200_H */

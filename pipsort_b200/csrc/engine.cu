@@ -1,0 +1,729 @@
+// pipsort_b200 engine: host side of the C-ABI declared in include/pipsort_b200.h.
+//
+// Owns the device copy of one locus, the accumulator store and a CUDA stream; launches the kernels in
+// score.cuh (generic, warp per union configuration) and exhaustive.cuh (register kernel, lane per
+// union subset).  No CPU compute path exists: without a usable CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pipsort_b200.h"
+#include "common.cuh"
+#include "exhaustive.cuh"
+#include "score.cuh"
+
+using namespace pipsort;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess)                                                                  \
+            return fail(PIPSORT_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+u64 binom_host(int n, int k, bool* overflow) {
+    if (k < 0 || k > n) return 0;
+    unsigned __int128 v = 1;
+    for (int i = 1; i <= k; i++) {
+        v = v * (unsigned)(n - k + i) / (unsigned)i;
+        if (v >> 63) { if (overflow) *overflow = true; return ~0ull >> 1; }
+    }
+    return (u64)v;
+}
+
+// ---- preparation kernels ------------------------------------------------------------------------------
+// W[i][j] = d * sigma[orig[i]][orig[j]]  (permutation into the internal order + the d_s scaling of
+// construct_diagC's diagonal, postcal.cpp:89,250,254-255)
+__global__ void gather_study_kernel(const double* __restrict__ sigma, int n_raw, const int* __restrict__ orig, int n,
+                                    int ldw, double d, double* __restrict__ W) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= ldw || i >= n) return;
+    double v = 0.0;
+    if (j < n) v = d * sigma[(size_t)orig[i] * n_raw + orig[j]];
+    W[(size_t)i * ldw + j] = v;
+}
+
+__global__ void study_vectors_kernel(const double* __restrict__ W, int ldw, const double* __restrict__ z_raw,
+                                     const int* __restrict__ orig, int n, double hd, double* __restrict__ A,
+                                     double* __restrict__ z, double* __restrict__ invA, double* __restrict__ u,
+                                     double* __restrict__ e1m, int* __restrict__ e1n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = 1.0 + W[(size_t)i * ldw + i];
+    const double zi = z_raw[orig[i]];
+    A[i] = a;
+    z[i] = zi;
+    invA[i] = 1.0 / a;
+    u[i] = zi / a;
+    double m;
+    int e;
+    xexp(hd * (zi * zi / a), m, e);
+    e1m[i] = m / sqrt(a);
+    e1n[i] = e;
+}
+
+// ---- finalize: bins -> log-space results --------------------------------------------------------------
+__device__ inline XAcc bins_read(const AccDev& a, int slot, int g) {
+    const double* p = bin_ptr(a, slot, g);
+    for (int b = a.NB - 1; b >= 0; b--) {
+        const double v = p[(size_t)b * a.Upad];
+        if (v > 0.0) {
+            double M = v;
+            if (b > 0) M += p[(size_t)(b - 1) * a.Upad] * 0x1p-512;
+            if (b > 1) M += (p[(size_t)(b - 2) * a.Upad] * 0x1p-512) * 0x1p-512;
+            int hi = __double2hiint(M);
+            int e = ((hi >> 20) & 0x7ff) - 1023;
+            M = __hiloint2double(hi - (e << 20), __double2loint(M));
+            return XAcc{M, 512 * b - a.bias + e};
+        }
+    }
+    return xacc_empty();
+}
+
+// log(M 2^N) + c ; 0.0 (the reference's "empty" sentinel, postcal.h:102-112) when nothing was added
+__device__ inline double xlog_or_zero(const XAcc& a, double c) {
+    if (!(a.M > 0.0)) return 0.0;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double n = (double)a.N;
+    return (n * LN2_HI + (log(a.M) + n * LN2_LO)) + c;
+}
+
+// res: [0] total, [1] noCausal[0], [2] noCausal[1], then 5 arrays of U (internal order):
+//      postValues study 0, postValues study 1, sharedPips, sharedLL, notSharedLL
+__global__ void finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < 3) res[g] = xlog_or_zero(bins_read(acc, SCAL, g), cx);
+    if (g >= U) return;
+    XAcc x1 = bins_read(acc, X1, g), x2 = bins_read(acc, X2, g), x3 = bins_read(acc, X3, g);
+    XAcc p0 = x1, p1 = x2;
+    xmerge(p0, x3);
+    xmerge(p1, x3);
+    double* r = res + 3;
+    r[g] = xlog_or_zero(p0, cx);
+    r[U + g] = xlog_or_zero(p1, cx);
+    r[2 * U + g] = xlog_or_zero(x3, cx);
+    r[3 * U + g] = xlog_or_zero(bins_read(acc, YS, g), cy);
+    r[4 * U + g] = xlog_or_zero(bins_read(acc, YN, g), cy);
+}
+
+__global__ void add_bins_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+// ---- FP64 peak micro-benchmark ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-9, x2 = x0 + 2e-9, x3 = x0 + 3e-9, x4 = x0 + 4e-9, x5 = x0 + 5e-9,
+           x6 = x0 + 6e-9, x7 = x0 + 7e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s;   // never true in practice; keeps the chains alive
+}
+
+}  // namespace
+
+struct pipsort_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    LocusDev L;
+    int U = 0, kb = 3, sm_count = 148;
+    int n_raw[2] = {0, 0};
+    double K = 0, gamma = 0, p = 0;
+    std::vector<int> perm;          // internal -> user union index
+    std::vector<int> orig[2];       // study-local (internal order) -> original study index
+    std::vector<int> loc[2];        // internal union index -> study-local index or -1
+    std::vector<int> types;         // internal union index -> 0 shared, 1 only study 0, 2 only study 1, 3 nowhere
+    std::vector<void*> allocs;
+    int* d_snp_map = nullptr;       // user order, [2][U]
+    double* d_res = nullptr;
+    std::vector<double> h_res;
+    size_t bins_len = 0;
+    u64 launches = 0;
+    // scratch for pipsort_score_union_configs (host buffers)
+    int* d_idx = nullptr; unsigned char* d_upd = nullptr; double* d_out = nullptr;
+    size_t cap_idx = 0, cap_upd = 0, cap_out = 0;
+    int score_smem_set = 0, exh_smem_set = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(pipsort_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    e->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+template <class T>
+int dev_upload(pipsort_engine* e, T** p, const T* src, size_t count) {
+    int rc = dev_alloc(e, p, count);
+    if (rc) return rc;
+    if (count) CU(cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+int ensure_score_smem(pipsort_engine* e, int ws_kmax, size_t* bytes) {
+    *bytes = SCORE_WARPS * warp_ws_bytes(ws_kmax);
+    if (e->score_smem_set < ws_kmax) {
+        size_t mx = SCORE_WARPS * warp_ws_bytes(KMAX);
+        CU(cudaFuncSetAttribute(score_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        CU(cudaFuncSetAttribute(exhaustive_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+        e->score_smem_set = KMAX;
+    }
+    return 0;
+}
+
+// number of expanded configurations of the subsets of size j whose smallest element is g, and of all
+// subsets of size j -- by elementary symmetric polynomials of the per-SNP state counts (3 / 1 / 0).
+struct WorkModel {
+    std::vector<std::vector<double>> E;  // E[m][g] = e_m(w_g .. w_{U-1})
+    std::vector<double> w;
+    int U;
+    WorkModel(const std::vector<int>& types, int c) : U((int)types.size()) {
+        w.resize(U);
+        for (int g = 0; g < U; g++) w[g] = types[g] == 0 ? 3.0 : (types[g] == 3 ? 0.0 : 1.0);
+        E.assign(c + 1, std::vector<double>(U + 1, 0.0));
+        for (int g = 0; g <= U; g++) E[0][g] = 1.0;
+        for (int m = 1; m <= c; m++)
+            for (int g = U - 1; g >= 0; g--) E[m][g] = E[m][g + 1] + w[g] * E[m - 1][g + 1];
+    }
+    double configs_first(int j, int g) const { return j == 0 ? 1.0 : w[g] * E[j - 1][g + 1]; }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* pipsort_last_error(void) { return g_err.c_str(); }
+const char* pipsort_version(void) { return "pipsort_b200 0.1 (sm_100a)"; }
+
+void pipsort_destroy(pipsort_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->d_idx) cudaFree(e->d_idx);
+    if (e->d_upd) cudaFree(e->d_upd);
+    if (e->d_out) cudaFree(e->d_out);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pipsort_engine* e) {
+    const int S = lc->num_studies, U = lc->union_count;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PIPSORT_E_CUDA, "no CUDA device available (the engine has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    e->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&e->ev0));
+    CU(cudaEventCreate(&e->ev1));
+    e->U = U;
+    e->K = lc->K; e->gamma = lc->gamma; e->p = lc->sharing_param;
+    e->kb = std::min(KMAX, std::max(3, lc->max_causal));
+
+    // ---- internal order ---------------------------------------------------------------------------
+    std::vector<int> type_user(U);
+    for (int g = 0; g < U; g++) {
+        const int a = lc->snp_map[g], b = lc->snp_map[U + g];
+        if (a >= lc->num_snps[0] || b >= lc->num_snps[1] || a < -1 || b < -1)
+            return fail(PIPSORT_E_ARG, "snp_map entry %d out of range", g);
+        type_user[g] = (a >= 0 && b >= 0) ? 0 : (a >= 0 ? 1 : (b >= 0 ? 2 : 3));
+    }
+    e->perm.resize(U);
+    for (int g = 0; g < U; g++) e->perm[g] = g;
+    if (!(flags & PIPSORT_KEEP_ORDER))
+        std::stable_sort(e->perm.begin(), e->perm.end(), [&](int a, int b) { return type_user[a] < type_user[b]; });
+    std::vector<int> u2i(U);
+    e->types.resize(U);
+    for (int i = 0; i < U; i++) { u2i[e->perm[i]] = i; e->types[i] = type_user[e->perm[i]]; }
+    for (int s = 0; s < S; s++) {
+        e->n_raw[s] = lc->num_snps[s];
+        e->loc[s].assign(U, -1);
+        e->orig[s].clear();
+        std::vector<char> seen(lc->num_snps[s], 0);
+        for (int i = 0; i < U; i++) {
+            const int o = lc->snp_map[(size_t)s * U + e->perm[i]];
+            if (o < 0) continue;
+            if (seen[o]) return fail(PIPSORT_E_ARG, "study %d SNP %d appears twice in the snp_map", s, o);
+            seen[o] = 1;
+            e->loc[s][i] = (int)e->orig[s].size();
+            e->orig[s].push_back(o);
+        }
+    }
+
+    // ---- device copy of the locus -------------------------------------------------------------------
+    LocusDev& L = e->L;
+    memset(&L, 0, sizeof L);
+    L.U = U;
+    int* d_tmp = nullptr;
+    int rc;
+    if ((rc = dev_upload(e, &d_tmp, u2i.data(), U))) return rc;
+    L.u2i = d_tmp;
+    if ((rc = dev_upload(e, &e->d_snp_map, lc->snp_map, (size_t)2 * U))) return rc;
+    size_t soff = 0, zoff = 0;
+    double maxexp_nats = 0.0, minexp_bits = 0.0;
+    for (int s = 0; s < S; s++) {
+        const int n_raw = lc->num_snps[s], n = (int)e->orig[s].size();
+        const int ldw = (n + 3) & ~3;
+        const double d = lc->d[s];
+        if (!(d > 0.0) || !std::isfinite(d)) return fail(PIPSORT_E_ARG, "d[%d] must be positive and finite", s);
+        double *d_sigma = nullptr, *d_zraw = nullptr, *W = nullptr, *A = nullptr, *z = nullptr, *invA = nullptr, *u = nullptr,
+               *e1m = nullptr;
+        int *d_orig = nullptr, *d_loc = nullptr, *e1n = nullptr;
+        CU(cudaMalloc(&d_sigma, std::max<size_t>((size_t)n_raw * n_raw, 1) * sizeof(double)));
+        CU(cudaMemcpyAsync(d_sigma, lc->sigma + soff, (size_t)n_raw * n_raw * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        if ((rc = dev_upload(e, &d_zraw, lc->z + zoff, n_raw))) return rc;
+        if ((rc = dev_upload(e, &d_orig, e->orig[s].data(), n))) return rc;
+        if ((rc = dev_upload(e, &d_loc, e->loc[s].data(), U))) return rc;
+        if ((rc = dev_alloc(e, &W, (size_t)n * ldw))) return rc;
+        if ((rc = dev_alloc(e, &A, n)) || (rc = dev_alloc(e, &z, n)) || (rc = dev_alloc(e, &invA, n)) ||
+            (rc = dev_alloc(e, &u, n)) || (rc = dev_alloc(e, &e1m, n)) || (rc = dev_alloc(e, &e1n, n)))
+            return rc;
+        if (n > 0) {
+            dim3 grid((ldw + 127) / 128, n);
+            gather_study_kernel<<<grid, 128, 0, e->stream>>>(d_sigma, n_raw, d_orig, n, ldw, d, W);
+            study_vectors_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(W, ldw, d_zraw, d_orig, n, 0.5 * d, A, z, invA, u, e1m, e1n);
+            e->launches += 2;
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaFree(d_sigma));
+        StudyDev& st = L.st[s];
+        st.W = W; st.A = A; st.z = z; st.invA = invA; st.u = u; st.e1m = e1m; st.e1n = e1n;
+        st.n = n; st.ldw = ldw; st.hd = 0.5 * d;
+        L.loc[s] = d_loc;
+        // exponent range: f_s(C) <= d/2 |z_C|^2 (A >= I), E_s(C) >= prod (1 + d Sigma_ii)^(-1/2)
+        std::vector<double> z2;
+        double maxdiag = 0.0;
+        for (int i = 0; i < n; i++) {
+            const int o = e->orig[s][i];
+            const double zi = lc->z[zoff + o];
+            z2.push_back(zi * zi);
+            maxdiag = std::max(maxdiag, std::fabs(lc->sigma[soff + (size_t)o * n_raw + o]));
+        }
+        std::sort(z2.begin(), z2.end(), std::greater<double>());
+        double top = 0.0;
+        for (int i = 0; i < std::min<int>(e->kb, (int)z2.size()); i++) top += z2[i];
+        maxexp_nats += 0.5 * d * top;
+        minexp_bits -= 0.5 * e->kb * std::log2(1.0 + d * maxdiag);
+        soff += (size_t)n_raw * n_raw;
+        zoff += n_raw;
+    }
+
+    // ---- prior tables (log_prior, postcal.cpp:19-59) --------------------------------------------------
+    const double gam = lc->gamma, p = lc->sharing_param;
+    if (!(gam > 0.0 && gam < 1.0)) return fail(PIPSORT_E_ARG, "gamma must be in (0,1)");
+    if (!(p >= 0.0 && p <= 1.0)) return fail(PIPSORT_E_ARG, "sharing_param must be in [0,1]");
+    double minpi = 0.0;
+    for (int j = 0; j <= KMAX; j++)
+        for (int a = 0; a <= j; a++) {
+            double lp = 0.0, rel = 0.0;
+            if (p != 0.0) {                                   // postcal.cpp:27: the sharing term is skipped for p == 0
+                for (int i = 0; i < a; i++) lp += std::log(p);
+                for (int i = a; i < j; i++) lp += std::log((1.0 - p) * 0.5);
+                rel = lp;
+            }
+            for (int i = 0; i < j; i++) lp += std::log(gam);
+            lp += (U - j) * std::log(1.0 - gam);
+            rel += j * (std::log(gam) - std::log(1.0 - gam));
+            L.logprior[j][a] = lp;
+            L.pi[j][a] = std::exp(rel);                       // 0 when p == 1 and a < j
+            if (j <= e->kb && std::isfinite(rel)) minpi = std::min(minpi, rel);
+        }
+    L.neg_half_K = -0.5 * lc->K;
+    L.null_l = (-lc->K / 2 - std::sqrt(std::fabs(1.0))) + U * std::log(1.0 - gam);   // postcal.cpp:802-803
+
+    // ---- expansion tables: digit i of e = state of SNP i (0: study 0 only, 1: study 1 only, 2: both) ---
+    for (int k = 0; k <= KMAX; k++) {
+        int n3 = 1;
+        for (int i = 0; i < k; i++) n3 *= 3;
+        std::vector<uint32_t> tab(n3);
+        for (int x = 0; x < n3; x++) {
+            uint32_t m0 = 0, m1 = 0, a = 0;
+            int v = x;
+            for (int i = 0; i < k; i++, v /= 3) {
+                const int t = v % 3;
+                if (t != 1) m0 |= 1u << i;
+                if (t != 0) m1 |= 1u << i;
+                if (t == 2) a++;
+            }
+            tab[x] = m0 | m1 << 8 | a << 16;
+        }
+        uint32_t* d_tab = nullptr;
+        if ((rc = dev_upload(e, &d_tab, tab.data(), n3))) return rc;
+        L.exptab[k] = d_tab;
+    }
+
+    // ---- accumulator store ------------------------------------------------------------------------------
+    const double maxexp_bits = maxexp_nats * 1.4426950408889634 + 128.0;
+    minexp_bits += minpi * 1.4426950408889634 - 128.0;
+    if (!(maxexp_bits < 1.0e8) || !(minexp_bits > -1.0e8))
+        return fail(PIPSORT_E_RANGE, "exponent range of the locus is out of bounds (z-scores / d too large?)");
+    AccDev& acc = L.acc;
+    acc.bias = (((int)std::ceil(-minexp_bits) + 511) / 512 + 1) * 512;
+    acc.NB = ((int)std::ceil(maxexp_bits) + acc.bias) / 512 + 2;
+    acc.Upad = std::max((U + 3) & ~3, 4);
+    e->bins_len = (size_t)NSLOT * acc.NB * acc.Upad;
+    if ((rc = dev_alloc(e, &acc.bins, e->bins_len))) return rc;
+    if ((rc = dev_alloc(e, &acc.counters, 2))) return rc;
+    if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U))) return rc;
+    e->h_res.resize(3 + (size_t)5 * U);
+    CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
+    CU(cudaMemsetAsync(acc.counters, 0, 2 * sizeof(u64), e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int pipsort_create(const pipsort_locus* lc, int device, uint32_t flags, pipsort_engine** out) {
+    if (!lc || !out) return fail(PIPSORT_E_ARG, "null argument");
+    *out = nullptr;
+    if (lc->num_studies != 2)
+        return fail(PIPSORT_E_STUDIES, "This prior only works with two studies right now");   // postcal.cpp:20-23
+    if (lc->union_count < 0 || !lc->num_snps || !lc->sigma || !lc->z || !lc->d || (!lc->snp_map && lc->union_count))
+        return fail(PIPSORT_E_ARG, "incomplete locus description");
+    if (lc->num_snps[0] < 0 || lc->num_snps[1] < 0) return fail(PIPSORT_E_ARG, "negative SNP count");
+    pipsort_engine* e = new pipsort_engine();
+    int rc = create_impl(lc, device, flags, e);
+    if (rc) { std::string keep = g_err; pipsort_destroy(e); g_err = keep; return rc; }
+    *out = e;
+    return 0;
+}
+
+int pipsort_reset(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(e->L.acc.bins, 0, e->bins_len * sizeof(double), e->stream));
+    CU(cudaMemsetAsync(e->L.acc.counters, 0, 2 * sizeof(u64), e->stream));
+    return 0;
+}
+
+int pipsort_total_ranks(const pipsort_engine* e, int c, uint64_t* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    if (c < 0) return fail(PIPSORT_E_ARG, "c must be >= 0");
+    u64 t = 0;
+    bool ovf = false;
+    for (int j = 0; j <= std::min(c, e->U); j++) {
+        t += binom_host(e->U, j, &ovf);
+        if (ovf || t >> 63) return fail(PIPSORT_E_RANGE, "rank space exceeds 2^63 (U=%d, c=%d)", e->U, c);
+    }
+    *out = t;
+    return 0;
+}
+
+int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64_t rank_end) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (c < 0 || c > e->kb) return fail(PIPSORT_E_ARG, "c=%d outside [0,%d] (max_causal given at create)", c, e->kb);
+    uint64_t total = 0;
+    int rc = pipsort_total_ranks(e, c, &total);
+    if (rc) return rc;
+    rank_end = std::min<uint64_t>(rank_end, total);
+    if (rank_begin >= rank_end) return 0;
+    CU(cudaSetDevice(e->device));
+    u64 off = 0;
+    for (int j = 0; j <= std::min(c, e->U); j++) {
+        const u64 cnt = binom_host(e->U, j, nullptr);
+        const u64 lo = std::max<u64>(rank_begin, off), hi = std::min<u64>(rank_end, off + cnt);
+        if (lo < hi) {
+            const u64 rb = lo - off, re = hi - off;
+            bool done = false;
+            if ((rc = exhaustive_launch(e->L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh_smem_set)))
+                return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            if (!done) {
+                size_t smem = 0;
+                const int wk = std::max(j, 1);
+                if ((rc = ensure_score_smem(e, wk, &smem))) return rc;
+                const int chunk = 16;
+                const u64 nchunks = (re - rb + chunk - 1) / chunk;
+                const int blocks = (int)std::min<u64>((nchunks + SCORE_WARPS - 1) / SCORE_WARPS, (u64)e->sm_count * 8);
+                exhaustive_generic_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, j, rb, re, chunk, wk);
+                e->launches++;
+                CU(cudaGetLastError());
+            }
+        }
+        off += cnt;
+    }
+    return 0;
+}
+
+int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
+                                       const uint8_t* d_make_updates, double* d_out) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (n < 0 || kmax < 0 || kmax > e->kb) return fail(PIPSORT_E_ARG, "kmax=%d outside [0,%d]", kmax, e->kb);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(e->device));
+    size_t smem = 0;
+    const int wk = std::max(kmax, 1);
+    int rc = ensure_score_smem(e, wk, &smem);
+    if (rc) return rc;
+    const int blocks = (int)std::min<int64_t>((n + SCORE_WARPS - 1) / SCORE_WARPS, (int64_t)e->sm_count * 8);
+    score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, d_idx, n, kmax, wk, d_make_updates, d_out);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n, int kmax, const uint8_t* make_updates,
+                                double* out_max_abs_l) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (n < 0 || kmax < 0 || kmax > e->kb) return fail(PIPSORT_E_ARG, "kmax=%d outside [0,%d]", kmax, e->kb);
+    if (n == 0) return 0;
+    if (!idx && kmax > 0) return fail(PIPSORT_E_ARG, "null idx");
+    CU(cudaSetDevice(e->device));
+    const size_t ni = (size_t)n * std::max(kmax, 1);
+    if (e->cap_idx < ni) { if (e->d_idx) cudaFree(e->d_idx); CU(cudaMalloc(&e->d_idx, ni * sizeof(int))); e->cap_idx = ni; }
+    if (e->cap_upd < (size_t)n) { if (e->d_upd) cudaFree(e->d_upd); CU(cudaMalloc(&e->d_upd, n)); e->cap_upd = n; }
+    if (e->cap_out < (size_t)n) { if (e->d_out) cudaFree(e->d_out); CU(cudaMalloc(&e->d_out, n * sizeof(double))); e->cap_out = n; }
+    if (kmax > 0) CU(cudaMemcpyAsync(e->d_idx, idx, (size_t)n * kmax * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if (make_updates) CU(cudaMemcpyAsync(e->d_upd, make_updates, n, cudaMemcpyHostToDevice, e->stream));
+    int rc = pipsort_score_union_configs_device(e, e->d_idx, n, kmax, make_updates ? e->d_upd : nullptr, e->d_out);
+    if (rc) return rc;
+    if (out_max_abs_l) CU(cudaMemcpyAsync(out_max_abs_l, e->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int check_flags(pipsort_engine* e) {
+    u64 c[2];
+    CU(cudaMemcpyAsync(c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (c[1] & ERR_NOT_PD) return fail(PIPSORT_E_SINGULAR, "matrix is singular");   // postcal.cpp:291-294
+    if (c[1] & ERR_RANGE) return fail(PIPSORT_E_RANGE, "a contribution fell outside the provisioned exponent range");
+    return 0;
+}
+
+int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    const int U = e->U;
+    const double cy = -0.5 * e->K, cx = cy + U * std::log(1.0 - e->gamma);
+    finalize_kernel<<<(std::max(U, 3) + 127) / 128, 128, 0, e->stream>>>(e->L.acc, U, cx, cy, e->d_res);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    int rc = check_flags(e);
+    if (rc) return rc;
+    const double* r = e->h_res.data();
+    if (out->total) *out->total = r[0];
+    if (out->noCausal) { out->noCausal[0] = r[1]; out->noCausal[1] = r[2]; }
+    r += 3;
+    if (out->postValues) {
+        const int N = e->n_raw[0] + e->n_raw[1];
+        for (int i = 0; i < N; i++) out->postValues[i] = 0.0;
+        int offs = 0;
+        for (int s = 0; s < 2; s++) {
+            for (int g = 0; g < U; g++)
+                if (e->loc[s][g] >= 0) out->postValues[offs + e->orig[s][e->loc[s][g]]] = r[(size_t)s * U + g];
+            offs += e->n_raw[s];
+        }
+    }
+    for (int g = 0; g < U; g++) {
+        const int ug = e->perm[g];
+        if (out->sharedPips) out->sharedPips[ug] = r[(size_t)2 * U + g];
+        if (out->sharedLL) out->sharedLL[ug] = r[(size_t)3 * U + g];
+        if (out->notSharedLL) out->notSharedLL[ug] = r[(size_t)4 * U + g];
+    }
+    return 0;
+}
+
+int pipsort_config_count(pipsort_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    u64 c = 0;
+    CU(cudaMemcpyAsync(&c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    *out = c;
+    return 0;
+}
+
+int pipsort_enumerate(pipsort_engine* e, int c, uint64_t rank, uint32_t expansion, int32_t* out_union_idx,
+                      int32_t* out_state, uint32_t* n_expansions) {
+    if (!e || !out_union_idx || !out_state) return fail(PIPSORT_E_ARG, "null argument");
+    if (c < 0 || c > KMAX) return fail(PIPSORT_E_ARG, "c=%d outside [0,%d]", c, KMAX);
+    uint64_t total = 0;
+    int rc = pipsort_total_ranks(e, c, &total);
+    if (rc) return rc;
+    if (rank >= total) return fail(PIPSORT_E_ARG, "rank out of range");
+    CU(cudaSetDevice(e->device));
+    int* d = nullptr;
+    CU(cudaMalloc(&d, (2 * KMAX + 1) * sizeof(int)));
+    enumerate_kernel<<<1, 32, 0, e->stream>>>(e->U, e->d_snp_map, c, rank, expansion, d, d + KMAX, (unsigned*)(d + 2 * KMAX));
+    e->launches++;
+    int h[2 * KMAX + 1];
+    cudaError_t err = cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    if (err != cudaSuccess) return fail(PIPSORT_E_CUDA, "enumerate failed: %s", cudaGetErrorString(err));
+    for (int i = 0; i < c; i++) { out_union_idx[i] = h[i]; out_state[i] = h[KMAX + i]; }
+    if (n_expansions) *n_expansions = (uint32_t)h[2 * KMAX];
+    return 0;
+}
+
+int pipsort_accumulator_buffer(pipsort_engine* e, void** device_ptr, uint64_t* num_doubles) {
+    if (!e || !device_ptr || !num_doubles) return fail(PIPSORT_E_ARG, "null argument");
+    *device_ptr = e->L.acc.bins;
+    *num_doubles = e->bins_len;
+    return 0;
+}
+
+int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
+    if (!dst || !src) return fail(PIPSORT_E_ARG, "null engine");
+    if (dst->bins_len != src->bins_len || dst->L.acc.bias != src->L.acc.bias || dst->U != src->U)
+        return fail(PIPSORT_E_ARG, "engines were not created from the same locus");
+    CU(cudaSetDevice(src->device));
+    CU(cudaStreamSynchronize(src->stream));
+    u64 cs[2], cd[2];
+    CU(cudaMemcpy(cs, src->L.acc.counters, sizeof cs, cudaMemcpyDeviceToHost));
+    CU(cudaSetDevice(dst->device));
+    double* tmp = nullptr;
+    const double* from = src->L.acc.bins;
+    if (src->device != dst->device) {
+        CU(cudaMalloc(&tmp, dst->bins_len * sizeof(double)));
+        CU(cudaMemcpyPeerAsync(tmp, dst->device, src->L.acc.bins, src->device, dst->bins_len * sizeof(double), dst->stream));
+        from = tmp;
+    }
+    add_bins_kernel<<<(unsigned)((dst->bins_len + 255) / 256), 256, 0, dst->stream>>>(dst->L.acc.bins, from, dst->bins_len);
+    dst->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(dst->stream));
+    if (tmp) CU(cudaFree(tmp));
+    CU(cudaMemcpy(cd, dst->L.acc.counters, sizeof cd, cudaMemcpyDeviceToHost));
+    cd[0] += cs[0];
+    cd[1] |= cs[1];
+    CU(cudaMemcpy(dst->L.acc.counters, cd, sizeof cd, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds) {
+    if (!e || !bounds || parts < 1) return fail(PIPSORT_E_ARG, "bad argument");
+    uint64_t total = 0;
+    int rc = pipsort_total_ranks(e, c, &total);
+    if (rc) return rc;
+    const int U = e->U, cc = std::min(c, U);
+    WorkModel wm(e->types, std::max(cc, 1));
+    // segments of consecutive ranks (size class j, smallest element g) with their work estimate
+    struct Seg { u64 begin, count; double work; };
+    std::vector<Seg> segs;
+    u64 off = 0;
+    const double per_subset = 8.0;   // Cholesky work is per union subset, the rest per expanded configuration
+    for (int j = 0; j <= cc; j++) {
+        if (j == 0) { segs.push_back({off, 1, 1.0}); off += 1; continue; }
+        for (int g = 0; g + j <= U; g++) {
+            const u64 cnt = binom_host(U - 1 - g, j - 1, nullptr);
+            segs.push_back({off, cnt, wm.configs_first(j, g) + per_subset * (double)cnt});
+            off += cnt;
+        }
+    }
+    double tw = 0.0;
+    for (const Seg& s : segs) tw += s.work;
+    bounds[0] = 0;
+    bounds[parts] = total;
+    size_t si = 0;
+    double acc = 0.0;
+    for (int p = 1; p < parts; p++) {
+        const double target = tw * p / parts;
+        while (si < segs.size() && acc + segs[si].work < target) acc += segs[si++].work;
+        u64 b = total;
+        if (si < segs.size()) {
+            const double frac = segs[si].work > 0 ? (target - acc) / segs[si].work : 0.0;
+            b = segs[si].begin + (u64)(frac * (double)segs[si].count);
+        }
+        bounds[p] = std::max<uint64_t>(bounds[p - 1], std::min<uint64_t>(b, total));
+    }
+    return 0;
+}
+
+void* pipsort_stream(pipsort_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int pipsort_sync(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int pipsort_timer_begin(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventRecord(e->ev0, e->stream));
+    return 0;
+}
+
+int pipsort_timer_end(pipsort_engine* e, float* ms) {
+    if (!e || !ms) return fail(PIPSORT_E_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventRecord(e->ev1, e->stream));
+    CU(cudaEventSynchronize(e->ev1));
+    CU(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return 0;
+}
+
+uint64_t pipsort_launch_count(const pipsort_engine* e) { return e ? e->launches : 0; }
+
+int pipsort_measure_fp64_peak(int device, double* flops_per_sec) {
+    if (!flops_per_sec) return fail(PIPSORT_E_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PIPSORT_E_CUDA, "no CUDA device available");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        CU(cudaEventRecord(a));
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1.0e-7);
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3));
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *flops_per_sec = best;
+    return 0;
+}
+
+}  // extern "C"

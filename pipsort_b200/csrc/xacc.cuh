@@ -1,0 +1,87 @@
+// Extended-range FP64 arithmetic for the PIPSORT posterior engine (sm_100a).
+//
+// The reference accumulates everything in log space (postcal.h:102-112, addlogSpace): one exp and
+// one log per update, under an OpenMP critical section.  The raw-log outputs (shared_ll /
+// notshared_ll columns, postcal.h:326) span thousands of nats inside one locus (tests/example:
+// -43204 ... -40675), so a single linear scale cannot represent them in a double.  Here every
+// weight exp(l) is carried as  m * 2^n  (m: non-negative double, n: int32) and every accumulator
+// ("XAcc") as  M * 2^N ;  an update is one integer subtract, one exponent-field construction and
+// one DFMA -- no exp, no log, no branch except the rare re-basing when a term is 2^512 larger than
+// the accumulator's base.  Logs are taken once per accumulator in the finalize kernel.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pipsort {
+
+constexpr int XNEG = -(1 << 28);  // exponent of an "empty" value; 3*XNEG still fits in int32
+
+struct XAcc {
+    double M;
+    int N;
+};
+
+__host__ __device__ __forceinline__ XAcc xacc_empty() { return XAcc{0.0, XNEG}; }
+
+// 2^e for e in [-1022, 1023], +0.0 below (flush), caller guarantees e <= 1023
+__device__ __forceinline__ double pow2c(int e) {
+    int hi = max(e + 1023, 0) << 20;
+    return __hiloint2double(hi, 0);
+}
+
+// acc += m * 2^n
+__device__ __forceinline__ void xadd(XAcc& a, double m, int n) {
+    int e = n - a.N;
+    if (e > 512) {  // re-base on the new (much larger) term; old content is scaled down (maybe to 0)
+        a.M *= pow2c(max(-e, -2000));
+        a.N = n;
+        e = 0;
+    }
+    a.M = fma(m, pow2c(e), a.M);
+}
+
+__device__ __forceinline__ void xmerge(XAcc& a, const XAcc& b) { xadd(a, b.M, b.N); }
+
+// exp(t) = m * 2^n with m in [0.70, 1.42];  |t| < 2^30 ln 2.  Cody-Waite reduction + degree-13
+// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18 relative).
+__device__ __forceinline__ void xexp(double t, double& m, int& n) {
+    const double LOG2E = 1.4426950408889634;
+    const double LN2_HI = 6.93147180369123816490e-01;  // low 21 bits zero: k*LN2_HI exact for |k| < 2^21..
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint + int extraction in one add
+    double tmp = fma(t, LOG2E, MAGIC);
+    n = __double2loint(tmp);
+    double kf = tmp - MAGIC;
+    double r = fma(-kf, LN2_HI, t);
+    r = fma(-kf, LN2_LO, r);
+    double p = 1.6059043836821613e-10;         // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);       // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);      // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);      // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);     // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);       // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);      // 1/7!
+    p = fma(p, r, 1.3888888888888889e-03);     // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);      // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);     // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);     // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    m = fma(p, r, 1.0);
+}
+
+// natural log of an accumulator; caller handles M == 0 (empty)
+__device__ __forceinline__ double xlog(const XAcc& a) { return log(a.M) + (double)a.N * 0.6931471805599453094; }
+
+// warp-wide sum of XAccs: common exponent = max N over the warp (one REDUX), mantissas re-scaled
+// to it (terms more than 2^1022 below the warp maximum flush to zero: they are below one ulp of
+// the sum), then a plain shuffle tree.  Result valid in every lane.
+__device__ __forceinline__ XAcc xwarp_sum(const XAcc& a) {
+    int nmax = __reduce_max_sync(0xffffffffu, a.N);
+    double v = a.M * pow2c(max(a.N - nmax, -2000));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return XAcc{v, nmax};
+}
+
+}  // namespace pipsort

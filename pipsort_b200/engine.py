@@ -1,0 +1,269 @@
+"""ctypes binding of the C-ABI in include/pipsort_b200.h (the engine itself is CUDA, csrc/).
+
+`Engine` mirrors the part of the reference's PostCal class that is the hot path (postcal.h:118-195,
+postcal.cpp:716-1092, sss_postcal.cpp:447-685): construct it from what the PostCal constructor
+receives, call compute_total_likelihood() / score_union_configs(), read the same result arrays.
+There is no CPU path: the library must load and a CUDA device must be present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+KEEP_ORDER = 1
+KMAX = 8
+
+
+class PipsortError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"pipsort_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Locus(C.Structure):
+    _fields_ = [("num_studies", C.c_int32), ("num_snps", C.POINTER(C.c_int32)), ("sigma", C.POINTER(C.c_double)),
+                ("z", C.POINTER(C.c_double)), ("d", C.POINTER(C.c_double)), ("K", C.c_double),
+                ("union_count", C.c_int32), ("snp_map", C.POINTER(C.c_int32)), ("gamma", C.c_double),
+                ("sharing_param", C.c_double), ("max_causal", C.c_int32)]
+
+
+class _Outputs(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_double)) for n in
+                ("total", "postValues", "noCausal", "sharedPips", "sharedLL", "notSharedLL")]
+
+
+def lib():
+    """Loads pipsort_b200/lib/libpipsort_b200.so (builds it first if the sources are newer)."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            path = _build.build_engine()
+        L = C.CDLL(path)
+        vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+        L.pipsort_create.argtypes = [C.POINTER(_Locus), i32, C.c_uint32, C.POINTER(vp)]
+        L.pipsort_destroy.argtypes = [vp]
+        L.pipsort_destroy.restype = None
+        L.pipsort_reset.argtypes = [vp]
+        L.pipsort_total_ranks.argtypes = [vp, i32, C.POINTER(u64)]
+        L.pipsort_run_exhaustive.argtypes = [vp, i32, u64, u64]
+        L.pipsort_score_union_configs.argtypes = [vp, C.POINTER(C.c_int32), C.c_int64, i32, C.POINTER(C.c_uint8),
+                                                  C.POINTER(C.c_double)]
+        L.pipsort_score_union_configs_device.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
+        L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
+        L.pipsort_config_count.argtypes = [vp, C.POINTER(u64)]
+        L.pipsort_enumerate.argtypes = [vp, i32, u64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_uint32)]
+        L.pipsort_accumulator_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+        L.pipsort_merge.argtypes = [vp, vp]
+        L.pipsort_shard_ranks.argtypes = [vp, i32, i32, C.POINTER(u64)]
+        L.pipsort_stream.argtypes = [vp]
+        L.pipsort_stream.restype = vp
+        L.pipsort_sync.argtypes = [vp]
+        L.pipsort_timer_begin.argtypes = [vp]
+        L.pipsort_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
+        L.pipsort_launch_count.argtypes = [vp]
+        L.pipsort_launch_count.restype = u64
+        L.pipsort_measure_fp64_peak.argtypes = [i32, C.POINTER(C.c_double)]
+        L.pipsort_last_error.restype = C.c_char_p
+        L.pipsort_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PipsortError(rc, lib().pipsort_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@dataclass
+class Results:
+    """PostCal's result members (postcal.h:62-99): log space, 0.0 = nothing accumulated."""
+    total: float
+    postValues: np.ndarray
+    noCausal: np.ndarray
+    sharedPips: np.ndarray
+    sharedLL: np.ndarray
+    notSharedLL: np.ndarray
+    n_configs: int = 0
+
+    @staticmethod
+    def _special_exp(x, total):           # postcal.h:277-283
+        with np.errstate(over="ignore"):
+            return np.where(x == 0, 0.0, np.exp(x - total))
+
+    def pips(self):
+        return self._special_exp(self.postValues, self.total)
+
+    def shared_pips(self):
+        return self._special_exp(self.sharedPips, self.total)
+
+    def no_causal(self):
+        return self._special_exp(self.noCausal, self.total)
+
+
+class Engine:
+    """Device-resident locus + accumulators (the hot-path half of the reference's PostCal)."""
+
+    def __init__(self, num_snps, sigma, z, d, K, snp_map, gamma=0.01, sharing_param=0.75, max_causal=3, device=0,
+                 keep_order=False):
+        self.num_snps = np.ascontiguousarray(num_snps, dtype=np.int32)
+        if isinstance(sigma, (list, tuple)):
+            sigma = np.concatenate([np.asarray(s, dtype=np.float64).ravel() for s in sigma])
+        if isinstance(z, (list, tuple)):
+            z = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in z])
+        sigma = np.ascontiguousarray(sigma, dtype=np.float64).ravel()
+        z = np.ascontiguousarray(z, dtype=np.float64).ravel()
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        smap = np.ascontiguousarray(snp_map, dtype=np.int32)
+        self.S = len(self.num_snps)
+        self.U = int(smap.shape[1]) if smap.ndim == 2 else 0
+        self.N = int(self.num_snps.sum())
+        assert sigma.size == int((self.num_snps.astype(np.int64) ** 2).sum()), "sigma size"
+        assert z.size == self.N, "z size"
+        loc = _Locus(self.S, self.num_snps.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sigma), _dp(z), _dp(d), float(K),
+                     self.U, smap.ctypes.data_as(C.POINTER(C.c_int32)), float(gamma), float(sharing_param),
+                     int(max_causal))
+        self._h = C.c_void_p()
+        _check(lib().pipsort_create(C.byref(loc), int(device), KEEP_ORDER if keep_order else 0, C.byref(self._h)))
+        self.max_causal = int(max_causal)
+        self.device = int(device)
+
+    # -- lifetime ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().pipsort_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- the hot path ----------------------------------------------------------------------------------
+    def reset(self):
+        _check(lib().pipsort_reset(self._h))
+
+    def total_ranks(self, c):
+        out = C.c_uint64()
+        _check(lib().pipsort_total_ranks(self._h, int(c), C.byref(out)))
+        return int(out.value)
+
+    def run_exhaustive(self, c, rank_begin=0, rank_end=None):
+        """computeTotalLikelihood (postcal.cpp:716) over union-subset ranks [rank_begin, rank_end); asynchronous."""
+        if rank_end is None:
+            rank_end = self.total_ranks(c)
+        _check(lib().pipsort_run_exhaustive(self._h, int(c), int(rank_begin), int(rank_end)))
+
+    def compute_total_likelihood(self, c=None):
+        """The reference's PostCal::computeTotalLikelihood: whole rank space, returns the results."""
+        c = self.max_causal if c is None else c
+        self.reset()
+        self.run_exhaustive(c)
+        return self.read()
+
+    def score_union_configs(self, idx, make_updates=None):
+        """expand_and_compute_lkl (sss_postcal.cpp:447) for a batch; returns max-|l| expansion per configuration."""
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        if idx.ndim == 1:
+            idx = idx.reshape(-1, 1)
+        n, kmax = idx.shape
+        out = np.zeros(n, dtype=np.float64)
+        mu = None
+        if make_updates is not None:
+            mu = np.ascontiguousarray(make_updates, dtype=np.uint8)
+            assert mu.size == n
+        _check(lib().pipsort_score_union_configs(
+            self._h, idx.ctypes.data_as(C.POINTER(C.c_int32)), n, kmax,
+            mu.ctypes.data_as(C.POINTER(C.c_uint8)) if mu is not None else None, _dp(out)))
+        return out
+
+    def score_union_configs_device(self, d_idx_ptr, n, kmax, d_upd_ptr, d_out_ptr):
+        _check(lib().pipsort_score_union_configs_device(self._h, C.c_void_p(d_idx_ptr), int(n), int(kmax),
+                                                        C.c_void_p(d_upd_ptr), C.c_void_p(d_out_ptr)))
+
+    def read(self) -> Results:
+        total = np.zeros(1)
+        post = np.zeros(self.N)
+        nc = np.zeros(self.S)
+        sp = np.zeros(self.U)
+        sl = np.zeros(self.U)
+        nl = np.zeros(self.U)
+        o = _Outputs(_dp(total), _dp(post), _dp(nc), _dp(sp), _dp(sl), _dp(nl))
+        _check(lib().pipsort_read_accumulators(self._h, C.byref(o)))
+        return Results(float(total[0]), post, nc, sp, sl, nl, self.config_count())
+
+    def config_count(self):
+        out = C.c_uint64()
+        _check(lib().pipsort_config_count(self._h, C.byref(out)))
+        return int(out.value)
+
+    def enumerate(self, c, rank, expansion=0):
+        idx = np.full(max(c, 1), -1, dtype=np.int32)
+        st = np.zeros(max(c, 1), dtype=np.int32)
+        ne = C.c_uint32()
+        _check(lib().pipsort_enumerate(self._h, int(c), int(rank), int(expansion),
+                                       idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       st.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(ne)))
+        k = int((idx[:c] >= 0).sum())
+        return idx[:k].tolist(), st[:k].tolist(), int(ne.value)
+
+    # -- multi-GPU plumbing ------------------------------------------------------------------------------
+    def accumulator_buffer(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        _check(lib().pipsort_accumulator_buffer(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def merge_from(self, other: "Engine"):
+        _check(lib().pipsort_merge(self._h, other._h))
+
+    def shard_ranks(self, c, parts):
+        b = (C.c_uint64 * (parts + 1))()
+        _check(lib().pipsort_shard_ranks(self._h, int(c), int(parts), b))
+        return [int(x) for x in b]
+
+    def stream(self):
+        return int(lib().pipsort_stream(self._h) or 0)
+
+    def sync(self):
+        _check(lib().pipsort_sync(self._h))
+
+    def timer_begin(self):
+        _check(lib().pipsort_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = C.c_float()
+        _check(lib().pipsort_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(lib().pipsort_launch_count(self._h))
+
+
+def measure_fp64_peak(device=0):
+    out = C.c_double()
+    _check(lib().pipsort_measure_fp64_peak(int(device), C.byref(out)))
+    return float(out.value)
+
+
+def version():
+    return lib().pipsort_version().decode()

@@ -74,3 +74,63 @@ def small_locus():
 @pytest.fixture(scope="session")
 def example_locus():
     return oracle_locus("example", p=0.25)
+
+
+# ---- GPU side ------------------------------------------------------------------------------------------
+def have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def engine_for(L, max_causal=3, **kw):
+    """pipsort_b200.Engine from an oracle Locus / SynthLocus (what crosses the C-ABI boundary)."""
+    import pipsort_b200 as P
+    n = getattr(L, "n_snps", None)
+    if n is None:
+        n = L.num_snps
+    p = getattr(L, "p", None)
+    if p is None:
+        p = L.sharing_param
+    return P.Engine(n, L.sigma, L.z, L.d, L.K, L.snp_map, gamma=L.gamma, sharing_param=p, max_causal=max_causal, **kw)
+
+
+def synth_as_oracle_locus(SL):
+    from oracle import oracle as O
+    return O.Locus(n_snps=SL.num_snps, sigma=SL.sigma, z=SL.z, K=SL.K, d=SL.d, snp_map=SL.snp_map, gamma=SL.gamma,
+                   p=SL.sharing_param)
+
+
+# log-likelihoods within 1e-10 relative, PIPs within 1e-8 absolute (BASELINE.json north_star)
+RTOL_LL = 1e-10
+ATOL_PIP = 1e-8
+
+
+def assert_results_match(got, want, rtol=RTOL_LL, atol_pip=ATOL_PIP):
+    """got: pipsort_b200.Results (or oracle Result); want: oracle Result / golden dict."""
+    import numpy as np
+    if isinstance(want, dict):
+        from oracle import oracle as O
+        want = O.Result(want["total"], np.array(want["post"]), np.array(want["noCausal"]), np.array(want["sharedPips"]),
+                        np.array(want["sharedLL"]), np.array(want["notSharedLL"]))
+    gp = getattr(got, "postValues", None)
+    if gp is None:
+        gp = got.post
+    if not hasattr(want, "post"):
+        want.post = want.postValues
+    assert got.total == pytest.approx(want.total, rel=rtol)
+    pairs = [("post", gp, want.post), ("noCausal", got.noCausal, want.noCausal),
+             ("sharedPips", got.sharedPips, want.sharedPips), ("sharedLL", got.sharedLL, want.sharedLL),
+             ("notSharedLL", got.notSharedLL, want.notSharedLL)]
+    for name, a, b in pairs:
+        a, b = np.asarray(a), np.asarray(b)
+        assert np.array_equal(a == 0, b == 0), f"{name}: empty pattern differs"
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=0, err_msg=name)
+    with np.errstate(over="ignore"):
+        def sx(x, t):
+            return np.where(np.asarray(x) == 0, 0.0, np.exp(np.asarray(x) - t))
+        np.testing.assert_allclose(sx(gp, got.total), sx(want.post, want.total), atol=atol_pip, rtol=0)
+        np.testing.assert_allclose(sx(got.sharedPips, got.total), sx(want.sharedPips, want.total), atol=atol_pip, rtol=0)
+        np.testing.assert_allclose(sx(got.noCausal, got.total), sx(want.noCausal, want.total), atol=atol_pip, rtol=0)

@@ -1,0 +1,236 @@
+"""Parity of the CUDA engine (through the C-ABI) with the CPU oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): log-likelihoods 1e-10 relative, PIPs / shared PIPs / no-causal
+probabilities 1e-8 absolute, enumeration and credible-set membership bit-exact.
+"""
+import itertools
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (GOLDEN, args_to_params, assert_results_match, engine_for, golden, has_golden, oracle_locus,
+                      synth_as_oracle_locus)
+
+pytestmark = pytest.mark.gpu
+
+EXH = ["small_c1_p075", "small_c2_p025", "small_c2_p075", "small_c3_p075", "small_c3_p0", "small_c3_g005_t1_s3",
+       "example_c1_p025", "example_c2_p025"]
+
+
+@pytest.mark.parametrize("keep_order", [False, True])
+@pytest.mark.parametrize("name", EXH)
+def test_exhaustive_matches_reference_dump(name, keep_order):
+    if not has_golden(name):
+        pytest.skip("golden not generated")
+    g = golden(name)
+    prm = args_to_params(g["args"])
+    L = oracle_locus(g["dataset"], p=prm["p"], gamma=prm["gamma"], s=prm["s"], t=prm["t"])
+    with engine_for(L, prm["c"], keep_order=keep_order) as e:
+        r = e.compute_total_likelihood(prm["c"])
+    assert_results_match(r, g)
+
+
+def test_counts_and_oracle_small():
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    with engine_for(L, 3) as e:
+        for c, n in [(0, 1), (1, 12), (2, 76), (3, 268)]:
+            r = e.compute_total_likelihood(c)
+            assert r.n_configs == O.exhaustive(L, c).n_eval
+            if c >= 2:
+                assert r.n_configs == n
+            assert_results_match(r, O.exhaustive(L, c))
+
+
+def fmt6(x):
+    return "%g" % x
+
+
+def test_example_expected_files():
+    """The six files the reference ships for tests/example (run_example.sh), from the engine's numbers."""
+    L = oracle_locus("example", p=0.25)
+    with engine_for(L, 2) as e:
+        r = e.compute_total_likelihood(2)
+    assert r.n_configs == 216817
+    d = os.path.join(GOLDEN, "example")
+    pips, off = r.pips(), 0
+    for s in range(2):
+        lines = ["SNP_ID\tProb_in_pCausalSet"] + [f"{nm}\t{fmt6(pips[off + i])}" for i, nm in enumerate(L.names[s])]
+        with open(os.path.join(d, f"expected_study{s}_post.txt")) as f:
+            assert f.read().splitlines() == lines
+        sel = [nm for i, nm in enumerate(L.names[s]) if pips[off + i] > 0.05]        # postcal.cpp:1158-1163
+        with open(os.path.join(d, f"expected_study{s}_set.txt")) as f:
+            assert f.read().splitlines() == sel                                        # credible set: bit-exact
+        off += len(L.names[s])
+    with open(os.path.join(d, "expected_nocausal.txt")) as f:
+        assert f.read().splitlines() == [fmt6(v) for v in r.no_causal()]
+    sp = r.shared_pips()
+    lines = ["SNP_ID\tshared_pip\tshared_ll\tnotshared_ll"] + [
+        f"{nm}\t{fmt6(sp[g])}\t{fmt6(r.sharedLL[g])}\t{fmt6(r.notSharedLL[g])}" for g, nm in enumerate(L.union_names)]
+    with open(os.path.join(d, "expected_shared_pips.txt")) as f:
+        assert f.read().splitlines() == lines
+
+
+def test_partial_rank_ranges_keep_order():
+    """With PIPSORT_KEEP_ORDER the rank space is the reference's: partial ranges equal the oracle's."""
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    tot = O.total_union_subsets(L.U, 3)
+    with engine_for(L, 3, keep_order=True) as e:
+        assert e.total_ranks(3) == tot
+        for lo, hi in [(0, 1), (0, 11), (5, 60), (56, 57), (30, tot), (tot - 1, tot), (7, 7)]:
+            e.reset()
+            e.run_exhaustive(3, lo, hi)
+            r = e.read()
+            want = O.exhaustive(L, 3, lo, hi)
+            assert r.n_configs == want.n_eval
+            assert_results_match(r, want)
+
+
+def test_shards_merge_to_whole():
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    whole = O.exhaustive(L, 3)
+    for parts in (2, 3, 8):
+        engines = [engine_for(L, 3) for _ in range(parts)]
+        b = engines[0].shard_ranks(3, parts)
+        assert b[0] == 0 and b[-1] == engines[0].total_ranks(3) and all(x <= y for x, y in zip(b, b[1:]))
+        for i, e in enumerate(engines):
+            e.run_exhaustive(3, b[i], b[i + 1])
+        for e in engines[1:]:
+            engines[0].merge_from(e)
+        r = engines[0].read()
+        assert r.n_configs == whole.n_eval
+        assert_results_match(r, whole)
+        for e in engines:
+            e.close()
+
+
+def test_enumeration_bit_exact():
+    """rank -> union subset and expansion -> per-study states, against the oracle's walk (nextBinary) and mask loop."""
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    with engine_for(L, 3) as e:
+        tot = e.total_ranks(3)
+        seq = [list(cmb) for j in range(4) for cmb in itertools.combinations(range(L.U), j)]
+        assert tot == len(seq)
+        for rank in list(range(0, 40)) + [56, 57, 100, tot - 1]:
+            idx, st, ne = e.enumerate(3, rank, 0)
+            assert idx == seq[rank] == O.walk(L.U, rank)
+            ex = O.expansions(L.snp_map, idx) if idx else np.zeros((1, 0), dtype=np.int32)
+            assert ne == len(ex)
+            for x in range(ne):
+                _, st, _ = e.enumerate(3, rank, x)
+                assert st == ex[x].tolist()
+    # a large rank space: U = 6000, c = 5 unranks without a walk
+    smap = np.stack([np.arange(6000), np.arange(6000)]).astype(np.int32)
+    import pipsort_b200 as P
+    n = np.array([6000, 6000], dtype=np.int32)
+    # tiny LD (identity) -- only the map matters for enumeration
+    with P.Engine([1, 1], [np.eye(1), np.eye(1)], [np.zeros(1), np.zeros(1)], [1.0, 1.0], 0.0,
+                  np.zeros((2, 6000), dtype=np.int32) - 1, max_causal=5) as e2:
+        tot = e2.total_ranks(5)
+        assert tot == O.total_union_subsets(6000, 5)
+        for rank in [0, 1, 6000, 6001, 12345678901, tot - 1]:
+            idx, _, _ = e2.enumerate(5, rank, 0)
+            assert idx == O.unrank(rank, 6000, 5)
+
+
+def _random_union_configs(rng, U, n, kmax):
+    idx = np.full((n, kmax), -1, dtype=np.int32)
+    for i in range(n):
+        k = int(rng.integers(0, kmax + 1))
+        idx[i, :k] = np.sort(rng.choice(U, k, replace=False))
+    return idx
+
+
+@pytest.mark.parametrize("dataset,kmax", [("small_example", 3), ("small_example", 5), ("example", 4)])
+def test_score_union_configs_matches_oracle(dataset, kmax):
+    """expand_and_compute_lkl for a batch: max-|l| outputs and accumulators, with make_updates on/off."""
+    from oracle import oracle as O
+    L = oracle_locus(dataset)
+    rng = np.random.default_rng(7)
+    idx = _random_union_configs(rng, L.U, 64, kmax)
+    idx[0, :] = -1                                   # the null configuration
+    upd = (rng.uniform(size=64) < 0.7).astype(np.uint8)
+    upd[0] = 1
+    want_l, want = O.score_union_configs(L, idx, upd)
+    with engine_for(L, kmax) as e:
+        got_l = e.score_union_configs(idx, upd)
+        r = e.read()
+        np.testing.assert_allclose(got_l, want_l, rtol=1e-10, atol=0)
+        assert_results_match(r, want)
+        # a second batch accumulates on top of the first (the SSS keeps one PostCal across iterations)
+        idx2 = _random_union_configs(rng, L.U, 33, kmax)
+        want_l2, want2 = O.score_union_configs(L, idx2, None, want)
+        got_l2 = e.score_union_configs(idx2)
+        np.testing.assert_allclose(got_l2, want_l2, rtol=1e-10, atol=0)
+        assert_results_match(e.read(), want2)
+
+
+def test_generic_and_register_paths_agree():
+    """All union subsets of size <= 3 scored through the generic (warp per configuration) kernel equal the
+    exhaustive driver's result (two independently written CUDA paths)."""
+    L = oracle_locus("small_example")
+    seq = [list(cmb) for j in range(4) for cmb in itertools.combinations(range(L.U), j)]
+    idx = np.full((len(seq), 3), -1, dtype=np.int32)
+    for i, s in enumerate(seq):
+        idx[i, :len(s)] = s
+    with engine_for(L, 3) as e:
+        a = e.compute_total_likelihood(3)
+        e.reset()
+        e.score_union_configs(idx)
+        b = e.read()
+    assert a.n_configs == b.n_configs
+    assert_results_match(a, b, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,overlap,c,p", [(12, 0.5, 3, 0.75), (40, 0.8, 3, 0.25), (60, 1.0, 2, 0.75), (30, 0.0, 3, 0.5),
+                                           (33, 0.8, 3, 0.0)])
+def test_synthetic_matches_oracle(n, overlap, c, p):
+    """Mixed SNP types (shared / study-specific), both SNP orders, against the oracle."""
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    SL = synth.make_locus(n, overlap=overlap, seed=1234 + n, sharing_param=p)
+    L = synth_as_oracle_locus(SL)
+    want = O.exhaustive(L, c)
+    assert want.n_eval == synth.count_configs(SL.snp_map, c)
+    for keep in (False, True):
+        with engine_for(SL, c, keep_order=keep) as e:
+            r = e.compute_total_likelihood(c)
+        assert r.n_configs == want.n_eval
+        assert_results_match(r, want)
+
+
+def test_full_size_properties():
+    """BASELINE configs at full size (150 SNPs/study c=3: 12,197,751 configurations; 300/study c=2) through
+    size-independent properties: configuration count, shard additivity, sum rules of the accumulators."""
+    from pipsort_b200 import synth
+    for n, c in [(150, 3), (300, 2)]:
+        SL = synth.make_locus(n, overlap=0.8)
+        with engine_for(SL, c) as e:
+            r = e.compute_total_likelihood(c)
+            assert r.n_configs == synth.count_configs(SL.snp_map, c)
+            # every configuration has between 1 and c causal union SNPs, except the null one:
+            #   sum_g (X1+X2+X3)[g] = sum_conf j(conf) w(conf)  in [total - null, c (total - null)]
+            pips = r.pips()
+            assert np.all(pips >= 0) and np.all(pips <= 1 + 1e-12)
+            nc = r.no_causal()
+            assert np.all(nc >= 0) and np.all(nc <= 1)
+            sp = r.shared_pips()
+            # shared PIP <= PIP in either study
+            smap = SL.snp_map
+            for g in range(SL.U):
+                if smap[0, g] >= 0 and smap[1, g] >= 0:
+                    assert sp[g] <= pips[smap[0, g]] + 1e-12 and sp[g] <= pips[n + smap[1, g]] + 1e-12
+                else:
+                    assert sp[g] == 0
+            # shards add up
+            b = e.shard_ranks(c, 4)
+            e.reset()
+            for i in range(4):
+                e.run_exhaustive(c, b[i], b[i + 1])
+            r2 = e.read()
+            assert r2.n_configs == r.n_configs
+            assert_results_match(r2, r, rtol=1e-12)
