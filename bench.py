@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- causal configurations / second of the exhaustive posterior calculation (BASELINE.json metric).
+
+A "step" is one pass of the hot path (PostCal::computeTotalLikelihood, postcal.cpp:716-1092) over one
+synthetic locus: reset accumulators, enumerate + score every union subset of size <= c in this rank's
+shard of the rank space, combine the accumulator stores of all ranks with ONE NCCL all-reduce(sum),
+finalize (bins -> log-space results).
+
+  value     whole-job configurations/s with the locus already resident in HBM, device-timed (CUDA events on
+            the stream everything is launched on), max over ranks
+  e2e       the same metric through the public API with HOST buffers: engine creation (H2D of LD / z / maps),
+            the pass, and the D2H read of the result arrays inside the timed region
+  roofline  FP64 vector-pipe roofline of the dominant kernel (the size-c class launch): algorithmic flops
+            (SURVEY.md 8d formula, counted exactly by class) / its device time / the DFMA peak measured here
+  cpu_baseline   the reference's own OpenMP CPU build (oracle/_ref/PIPSORT, unmodified sources) on this host,
+            on a bounded sample of the same workload (the size <= 2 prefix of the rank space, `-c 2`);
+            falls back to the OpenMP port of the oracle when the reference binary is not present
+
+python bench.py --impl reference ... times only the reference CPU implementation and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (SNPs per study, overlap, c)   -- BASELINE.json configs[3] / configs[2] / the saturating B10 of SURVEY 8d
+    "B150c3": (150, 0.8, 3),
+    "A300c2": (300, 0.8, 2),
+    "B1500c3": (1500, 0.8, 3),
+}
+METRIC = "causal configurations/sec (exhaustive, c=3, synthetic 150-SNP/study two-ancestry locus)"
+UNIT = "configs/s"
+
+
+def class_flops(snp_map, c):
+    """(algorithmic flops, configurations) of the size-c class and of the whole run."""
+    from pipsort_b200 import synth
+    tot, ntot = synth.flops_per_config_total(snp_map, c)
+    low, nlow = synth.flops_per_config_total(snp_map, c - 1) if c > 0 else (0.0, 0)
+    return (tot - low, ntot - nlow), (tot, ntot)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            with open(self.path) as f:
+                for line in f:
+                    t = [x.strip() for x in line.split(",")]
+                    if len(t) < 9:
+                        continue
+                    try:
+                        sm.append(float(t[1])); mx.append(float(t[2]))
+                    except ValueError:
+                        continue
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arms (test infrastructure: the only place bench.py executes anything under oracle/)
+# ---------------------------------------------------------------------------------------------------------
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "PIPSORT")
+
+
+def reference_cpu_run(L, c_sample, workdir):
+    """One run of the UNMODIFIED reference CLI (exhaustive, `-c c_sample`) on the locus; returns
+    (configurations, seconds of its own 'Time to eval all' timer, wall seconds)."""
+    from pipsort_b200 import synth
+    ld, z, mp, ns = synth.write_files(L, os.path.join(workdir, "in"))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    t = time.time()
+    p = subprocess.run([REF_BIN, "-l", ld, "-z", z, "-m", mp, "-n", ns, "-o", os.path.join(workdir, "out"), "-c",
+                        str(c_sample), "-g", repr(L.gamma), "-p", repr(L.sharing_param)], capture_output=True,
+                       text=True, env=env, cwd=workdir)
+    wall = time.time() - t
+    if p.returncode != 0:
+        raise RuntimeError("reference CLI failed: " + p.stderr[-500:])
+    m = re.search(r"Time to eval all=\s*(\d+)\[", p.stdout)
+    secs = int(m.group(1)) * 1e-6 if m else wall
+    return synth.count_configs(L.snp_map, c_sample), secs, wall
+
+
+def port_cpu_run(L, c, seconds_target=10.0):
+    """OpenMP port of the oracle on a rank sub-range sized to ~seconds_target; returns (configs, seconds, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synth_as_oracle_locus
+    from oracle import oracle as O
+    OL = synth_as_oracle_locus(L)
+    cores = os.cpu_count() or 1
+    tot = O.total_union_subsets(OL.U, c)
+    n = min(tot, 20000)
+    lo = tot - n                                  # the size-c class dominates; sample from its end
+    t = time.time(); _, ne = O.exhaustive_omp(OL, c, lo, tot, cores); dt = time.time() - t
+    if dt < seconds_target / 4 and n < tot:       # scale the sample up once
+        n = int(min(tot, n * seconds_target / max(dt, 1e-3)))
+        lo = tot - n
+        t = time.time(); _, ne = O.exhaustive_omp(OL, c, lo, tot, cores); dt = time.time() - t
+    return ne, dt, cores, f"union-subset ranks [{lo},{tot}) of {tot}"
+
+
+def cpu_baseline(L, c):
+    cores = os.cpu_count() or 1
+    if os.path.exists(REF_BIN):
+        try:
+            with tempfile.TemporaryDirectory() as tmp:
+                n, secs, wall = reference_cpu_run(L, c - 1, tmp)
+            return {"value": n / secs, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": f"unmodified reference CLI `-c {c - 1}` on the same locus = the size<={c - 1} prefix of the "
+                              f"rank space ({n} configurations); its own 'Time to eval all' {secs:.2f} s (wall {wall:.2f} s); "
+                              f"the reference forces 64 OpenMP threads (postcal.cpp:748) on {cores} host cores"}
+        except Exception as ex:  # fall through to the port
+            err = str(ex)[:200]
+    else:
+        err = "oracle/_ref/PIPSORT not built"
+    ne, dt, cores, what = port_cpu_run(L, c)
+    return {"value": ne / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"OpenMP port of the oracle (closed-form O(k^3) likelihood), {what}, {ne} configurations in {dt:.2f} s ({err})"}
+
+
+def run_reference_arm(args, L, c, wl):
+    """bench.py --impl reference: rank 0 alone times the reference's own CPU implementation."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    budget = 240.0
+    vals, walls = [], []
+    kind = "reference" if os.path.exists(REF_BIN) else "port"
+    sample = ""
+    t_all = time.time()
+    steps_done = 0
+    for i in range(args.warmup + args.steps):
+        timed = i >= args.warmup
+        if kind == "reference":
+            with tempfile.TemporaryDirectory() as tmp:
+                n, secs, wall = reference_cpu_run(L, c - 1, tmp)
+            sample = (f"unmodified reference CLI `-c {c - 1}` = size<={c - 1} prefix of the rank space, {n} configurations per step; "
+                      f"64 OpenMP threads forced by the reference on {cores} cores; timed with its own 'Time to eval all'")
+        else:
+            n, secs, cores, what = port_cpu_run(L, c)
+            sample = f"oracle OpenMP port, {what}"
+        if timed:
+            vals.append(n / secs); walls.append(secs); steps_done += 1
+        elapsed = time.time() - t_all
+        per = elapsed / (i + 1)
+        if elapsed + per > budget:          # keep the whole arm within a few minutes
+            if not timed:
+                continue_from = args.warmup  # skip remaining warm-ups (a fresh process has nothing to warm)
+                if i + 1 < continue_from:
+                    args.warmup = i + 1
+            elif steps_done >= 1:
+                break
+    if not vals:
+        n, secs, wall = reference_cpu_run(L, c - 1, tempfile.mkdtemp()) if kind == "reference" else port_cpu_run(L, c)[:3]
+        vals, walls, steps_done = [n / secs], [secs], 1
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_desc(wl, L, c), "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def wl_desc(wl, L, c):
+    sh, o0, o1 = L.n_types()
+    return (f"{wl}: synthetic two-ancestry locus, {int(L.num_snps[0])}+{int(L.num_snps[1])} SNPs, U={L.U} "
+            f"({sh} shared, {o0}+{o1} study-specific), exhaustive c={c}, p={L.sharing_param}, gamma={L.gamma}, seed 20261018")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="B150c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sat", action="store_true", help="skip the saturating B1500c3 side measurement")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from pipsort_b200 import synth
+    n_per, overlap, c = WORKLOADS[args.workload]
+    L = synth.make_locus(n_per, overlap=overlap)
+    if args.impl == "reference":
+        run_reference_arm(args, L, c, args.workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pipsort_b200 as P
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    # everything (engine kernels, NCCL all-reduce, timing events) is enqueued on ONE non-default stream
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure(L, c, steps, warmup, clocks=False):
+        """Device-timed steps on the resident locus; returns dict of timings."""
+        total_configs = synth.count_configs(L.snp_map, c)
+        e = P.Engine(L.num_snps, L.sigma, L.z, L.d, L.K, L.snp_map, gamma=L.gamma, sharing_param=L.sharing_param,
+                     max_causal=c, device=local)
+        stream = torch.cuda.current_stream()
+        e.set_stream(stream.cuda_stream)
+        b = e.shard_ranks(c, world)
+        lo, hi = b[rank], b[rank + 1]
+        acc = e.accumulator_tensor()
+
+        def step():
+            e.reset()
+            e.run_exhaustive(c, lo, hi)
+            if world > 1:
+                dist.all_reduce(acc)          # ONE NCCL collective on the accumulator store
+            e.finalize()
+
+        for _ in range(warmup):
+            e.flush_l2(); step()
+        barrier()
+        sampler = ClockSampler(local)
+        if clocks and rank == 0:
+            sampler.start()
+        l0 = e.launch_count()
+        evs, kms = [], []
+        t_wall = time.perf_counter()
+        for _ in range(steps):
+            e.flush_l2()                      # L2 flushed between timed iterations (outside the event pair)
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); step(); z.record(stream)
+            evs.append((a, z))
+            kms.append(None)
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        clk = sampler.stop() if clocks and rank == 0 else None
+        launches = e.launch_count() - l0
+        ms = [a.elapsed_time(z) for a, z in evs]
+        # dominant-kernel duration: a few extra steps timed on the launch itself
+        for _ in range(min(steps, 10)):
+            e.flush_l2(); step(); kms.append(e.last_kernel_ms())
+        kms = [k for k in kms if k is not None]
+        tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        k_ms = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
+        cnt = torch.tensor([e.config_count()], dtype=torch.int64, device=dev)   # last step's count on this rank
+        if world > 1:
+            dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt)
+        res = e.read() if rank == 0 else None
+        e.close()
+        assert int(cnt.item()) == total_configs, (int(cnt.item()), total_configs)
+        return dict(total_configs=total_configs, ms_per_step=float(tot_ms.item()) / steps, kernel_ms=float(k_ms.item()),
+                    launches=launches, wall_ms_per_step=1e3 * t_wall / steps, clocks=clk, result=res)
+
+    def measure_e2e(L, c, steps, warmup):
+        """Public API with HOST (pinned) buffers: create (H2D) + pass + read (D2H) + destroy, wall clock between syncs."""
+        total_configs = synth.count_configs(L.snp_map, c)
+        sig = torch.from_numpy(np.concatenate([s.ravel() for s in L.sigma])).pin_memory()
+        z = torch.from_numpy(np.concatenate(L.z)).pin_memory()
+        h2d = sig.numel() * 8 + z.numel() * 8 + L.snp_map.size * 4 * 3 + 2 * 16
+        d2h = 8 * (1 + 2 + L.N + 3 * L.U)
+
+        def once():
+            e = P.Engine(L.num_snps, sig.numpy(), z.numpy(), L.d, L.K, L.snp_map, gamma=L.gamma,
+                         sharing_param=L.sharing_param, max_causal=c, device=local)
+            b = e.shard_ranks(c, world)
+            e.run_exhaustive(c, b[rank], b[rank + 1])
+            if world > 1:
+                e.sync()
+                dist.all_reduce(e.accumulator_tensor())
+                torch.cuda.synchronize()
+            r = e.read()
+            e.close()
+            return r
+
+        for _ in range(warmup):
+            once()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(steps):
+            r = once()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return {"value": total_configs * steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()) / steps,
+                "timing": "host wall clock between device synchronisations, max over ranks (the call includes host work)"}
+
+    peak = P.measure_fp64_peak(local)                      # FLOP/s, DFMA chains on every SM
+    main_m = measure(L, c, args.steps, args.warmup, clocks=True)
+    e2e = measure_e2e(L, c, max(3, min(args.steps, 10)), 2)
+    (cf, cn), (tf, tn) = class_flops(L.snp_map, c)
+    value = main_m["total_configs"] / (main_m["ms_per_step"] * 1e-3)
+    # the dominant launch on rank r covers 1/world of the class (work-weighted shard)
+    achieved = cf / world / (main_m["kernel_ms"] * 1e-3) / 1e12
+    roof = {"bound": "fp64", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
+            "traffic": None,
+            "note": ("FP64 vector pipe (DFMA), no tensor cores / not HBM bound; achieved = ALGORITHMIC flops of the size-c class "
+                     f"({cf:.4g} flop, {cf / max(cn, 1):.1f}/configuration, SURVEY.md 8d) per launch / its CUDA-event duration "
+                     f"({main_m['kernel_ms']:.4f} ms); peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
+                     "figure; nominal 37 TFLOP/s). The kernel shares Cholesky work between the expansions of a union subset, so it "
+                     "executes fewer flops than the algorithmic count: frac can exceed 1; executed FP64 pipe utilisation is in profiles/.")}
+    sat = None
+    if not args.no_sat and args.workload == "B150c3":
+        Ls = synth.make_locus(1500, overlap=0.8)
+        sm = measure(Ls, 3, 3, 1)
+        (scf, scn), _ = class_flops(Ls.snp_map, 3)
+        sach = scf / world / (sm["kernel_ms"] * 1e-3) / 1e12
+        sat = {"workload": wl_desc("B1500c3", Ls, 3), "configs": sm["total_configs"], "ms_per_step": sm["ms_per_step"],
+               "value": sm["total_configs"] / (sm["ms_per_step"] * 1e-3), "unit": UNIT,
+               "roofline": {"bound": "fp64", "achieved": sach, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": sach / (peak / 1e12)}}
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cpu = cpu_baseline(L, c)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl_desc(args.workload, L, c), "configs_per_step": main_m["total_configs"],
+                           "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
+                           "sharding": f"rank space split into {world} work-weighted contiguous ranges, one NCCL all-reduce(sum) "
+                                       "of the accumulator store per step" if world > 1 else "single GPU"},
+                "clocks": main_m["clocks"], "e2e": e2e, "gpu_launches": main_m["launches"], "roofline": roof,
+                "locus_wall_ms": e2e["ms_per_step"], "wall_ms_per_step": main_m["wall_ms_per_step"]}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if sat is not None:
+            line["saturating"] = sat
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

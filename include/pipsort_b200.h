@@ -34,6 +34,9 @@ extern "C" {
 #define PIPSORT_KEEP_ORDER 1u /* keep the snp_map order internally (default: union SNPs are relabelled
                                  by type so that warps run one code path; sums are order independent) */
 
+#define PIPSORT_GENERIC_ONLY 2u /* testing: run every subset-size class through the generic (warp per configuration)
+                                  kernel instead of the register kernel                                */
+
 typedef struct pipsort_engine pipsort_engine;
 
 /* Locus description = the PostCal constructor arguments the likelihood actually consumes
@@ -111,6 +114,14 @@ int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, 
  * findOptimalSetGreedy (postcal.cpp:1144-1163) and printPost2File (postcal.h:288-336).            */
 int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out);
 
+/* Launches the finalize kernel only (bins -> log-space results, kept on the device); pipsort_read_accumulators
+ * = pipsort_finalize + device-to-host copy + scatter into the caller's arrays.                      */
+int pipsort_finalize(pipsort_engine* e);
+
+/* Device time (CUDA events on the engine's stream) of the dominant kernel of the last pipsort_run_exhaustive
+ * call: the launch that covered the largest subset-size class.  Blocks until that launch has finished. */
+int pipsort_last_kernel_ms(pipsort_engine* e, float* ms);
+
 /* Number of expanded configurations accumulated since the last reset (the reference's mycount). */
 int pipsort_config_count(pipsort_engine* e, uint64_t* out);
 
@@ -133,9 +144,15 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copi
  * weighted); bounds receives parts+1 values.                                                      */
 int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds);
 
-/* Stream the engine works on (cudaStream_t as void*), and a blocking sync on it. */
+/* Stream the engine works on (cudaStream_t as void*), and a blocking sync on it.  pipsort_set_stream
+ * makes the engine issue all further work on a caller-owned stream (e.g. the one a NCCL all-reduce of
+ * pipsort_accumulator_buffer is enqueued on); NULL restores the engine's own stream.                */
 void* pipsort_stream(pipsort_engine* e);
+int pipsort_set_stream(pipsort_engine* e, void* cuda_stream);
 int pipsort_sync(pipsort_engine* e);
+
+/* Benchmark hygiene: evict L2 by overwriting a scratch buffer larger than L2 on the engine's stream. */
+int pipsort_flush_l2(pipsort_engine* e);
 
 /* Device-side timing of the launches issued between begin and end (CUDA events on the engine's
  * stream): milliseconds.                                                                          */

@@ -149,8 +149,10 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 
 struct pipsort_engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    void* l2_scratch = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    bool evk_valid = false;
     LocusDev L;
     int U = 0, kb = 3, sm_count = 148;
     int n_raw[2] = {0, 0};
@@ -168,7 +170,9 @@ struct pipsort_engine {
     // scratch for pipsort_score_union_configs (host buffers)
     int* d_idx = nullptr; unsigned char* d_upd = nullptr; double* d_out = nullptr;
     size_t cap_idx = 0, cap_upd = 0, cap_out = 0;
-    int score_smem_set = 0, exh_smem_set = 0;
+    int score_smem_set = 0;
+    ExhScratch exh;
+    bool use_reg_kernel = true;
 };
 
 namespace {
@@ -235,7 +239,12 @@ void pipsort_destroy(pipsort_engine* e) {
     if (e->d_out) cudaFree(e->d_out);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->evk0) cudaEventDestroy(e->evk0);
+    if (e->evk1) cudaEventDestroy(e->evk1);
+    if (e->l2_scratch) cudaFree(e->l2_scratch);
+    if (e->exh.d_prefix) cudaFree(e->exh.d_prefix);
+    if (e->exh.d_counter) cudaFree(e->exh.d_counter);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
 
@@ -250,12 +259,16 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     e->sm_count = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
+    CU(cudaEventCreate(&e->evk0));
+    CU(cudaEventCreate(&e->evk1));
     e->U = U;
     e->K = lc->K; e->gamma = lc->gamma; e->p = lc->sharing_param;
     e->kb = std::min(KMAX, std::max(3, lc->max_causal));
+    e->use_reg_kernel = !(flags & PIPSORT_GENERIC_ONLY);
 
     // ---- internal order ---------------------------------------------------------------------------
     std::vector<int> type_user(U);
@@ -455,6 +468,16 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     rank_end = std::min<uint64_t>(rank_end, total);
     if (rank_begin >= rank_end) return 0;
     CU(cudaSetDevice(e->device));
+    e->evk_valid = false;
+    int jdom = 0;   // the largest subset-size class the range touches: its launch is the dominant kernel
+    {
+        u64 o = 0;
+        for (int j = 0; j <= std::min(c, e->U); j++) {
+            const u64 cnt = binom_host(e->U, j, nullptr);
+            if (std::max<u64>(rank_begin, o) < std::min<u64>(rank_end, o + cnt)) jdom = j;
+            o += cnt;
+        }
+    }
     u64 off = 0;
     for (int j = 0; j <= std::min(c, e->U); j++) {
         const u64 cnt = binom_host(e->U, j, nullptr);
@@ -462,7 +485,9 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
         if (lo < hi) {
             const u64 rb = lo - off, re = hi - off;
             bool done = false;
-            if ((rc = exhaustive_launch(e->L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh_smem_set)))
+            const bool dominant = j == jdom;
+            if (dominant) CU(cudaEventRecord(e->evk0, e->stream));
+            if (e->use_reg_kernel && (rc = exhaustive_launch(e->L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh)))
                 return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             if (!done) {
                 size_t smem = 0;
@@ -475,6 +500,7 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
                 e->launches++;
                 CU(cudaGetLastError());
             }
+            if (dominant) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
         }
         off += cnt;
     }
@@ -527,14 +553,31 @@ static int check_flags(pipsort_engine* e) {
     return 0;
 }
 
-int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
-    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+int pipsort_finalize(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     const int U = e->U;
     const double cy = -0.5 * e->K, cx = cy + U * std::log(1.0 - e->gamma);
     finalize_kernel<<<(std::max(U, 3) + 127) / 128, 128, 0, e->stream>>>(e->L.acc, U, cx, cy, e->d_res);
     e->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int pipsort_last_kernel_ms(pipsort_engine* e, float* ms) {
+    if (!e || !ms) return fail(PIPSORT_E_ARG, "null argument");
+    if (!e->evk_valid) return fail(PIPSORT_E_ARG, "no exhaustive launch recorded");
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventSynchronize(e->evk1));
+    CU(cudaEventElapsedTime(ms, e->evk0, e->evk1));
+    return 0;
+}
+
+int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    int rcf = pipsort_finalize(e);
+    if (rcf) return rcf;
+    const int U = e->U;
     CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     int rc = check_flags(e);
     if (rc) return rc;
@@ -669,6 +712,23 @@ int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bou
 }
 
 void* pipsort_stream(pipsort_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+int pipsort_set_stream(pipsort_engine* e, void* cuda_stream) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+int pipsort_flush_l2(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)256 << 20;   // L2 is 126 MB
+    if (!e->l2_scratch) CU(cudaMalloc(&e->l2_scratch, bytes));
+    CU(cudaMemsetAsync(e->l2_scratch, 0x5a, bytes, e->stream));
+    return 0;
+}
 
 int pipsort_sync(pipsort_engine* e) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");

@@ -18,6 +18,7 @@ from . import build as _build
 _lib = None
 
 KEEP_ORDER = 1
+GENERIC_ONLY = 2
 KMAX = 8
 
 
@@ -58,6 +59,8 @@ def lib():
                                                   C.POINTER(C.c_double)]
         L.pipsort_score_union_configs_device.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
         L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
+        L.pipsort_finalize.argtypes = [vp]
+        L.pipsort_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pipsort_config_count.argtypes = [vp, C.POINTER(u64)]
         L.pipsort_enumerate.argtypes = [vp, i32, u64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_uint32)]
@@ -67,6 +70,8 @@ def lib():
         L.pipsort_stream.argtypes = [vp]
         L.pipsort_stream.restype = vp
         L.pipsort_sync.argtypes = [vp]
+        L.pipsort_set_stream.argtypes = [vp, vp]
+        L.pipsort_flush_l2.argtypes = [vp]
         L.pipsort_timer_begin.argtypes = [vp]
         L.pipsort_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
         L.pipsort_launch_count.argtypes = [vp]
@@ -117,7 +122,7 @@ class Engine:
     """Device-resident locus + accumulators (the hot-path half of the reference's PostCal)."""
 
     def __init__(self, num_snps, sigma, z, d, K, snp_map, gamma=0.01, sharing_param=0.75, max_causal=3, device=0,
-                 keep_order=False):
+                 keep_order=False, generic_only=False):
         self.num_snps = np.ascontiguousarray(num_snps, dtype=np.int32)
         if isinstance(sigma, (list, tuple)):
             sigma = np.concatenate([np.asarray(s, dtype=np.float64).ravel() for s in sigma])
@@ -136,7 +141,7 @@ class Engine:
                      self.U, smap.ctypes.data_as(C.POINTER(C.c_int32)), float(gamma), float(sharing_param),
                      int(max_causal))
         self._h = C.c_void_p()
-        _check(lib().pipsort_create(C.byref(loc), int(device), KEEP_ORDER if keep_order else 0, C.byref(self._h)))
+        _check(lib().pipsort_create(C.byref(loc), int(device), (KEEP_ORDER if keep_order else 0) | (GENERIC_ONLY if generic_only else 0), C.byref(self._h)))
         self.max_causal = int(max_causal)
         self.device = int(device)
 
@@ -211,6 +216,14 @@ class Engine:
         _check(lib().pipsort_read_accumulators(self._h, C.byref(o)))
         return Results(float(total[0]), post, nc, sp, sl, nl, self.config_count())
 
+    def finalize(self):
+        _check(lib().pipsort_finalize(self._h))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _check(lib().pipsort_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def config_count(self):
         out = C.c_uint64()
         _check(lib().pipsort_config_count(self._h, C.byref(out)))
@@ -246,6 +259,22 @@ class Engine:
 
     def sync(self):
         _check(lib().pipsort_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        _check(lib().pipsort_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
+    def flush_l2(self):
+        _check(lib().pipsort_flush_l2(self._h))
+
+    def accumulator_tensor(self):
+        """Zero-copy torch view of the accumulator store (for torch.distributed all_reduce)."""
+        import torch
+        ptr, n = self.accumulator_buffer()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_View(), device=f"cuda:{self.device}")
 
     def timer_begin(self):
         _check(lib().pipsort_timer_begin(self._h))

@@ -31,6 +31,17 @@ def test_exhaustive_matches_reference_dump(name, keep_order):
     assert_results_match(r, g)
 
 
+def test_generic_only_flag_matches():
+    """PIPSORT_GENERIC_ONLY routes every size class through the warp-per-configuration kernel."""
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    want = O.exhaustive(L, 3)
+    with engine_for(L, 3, generic_only=True) as e:
+        r = e.compute_total_likelihood(3)
+    assert r.n_configs == want.n_eval
+    assert_results_match(r, want)
+
+
 def test_counts_and_oracle_small():
     from oracle import oracle as O
     L = oracle_locus("small_example")
