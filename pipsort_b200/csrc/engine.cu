@@ -154,6 +154,7 @@ struct pipsort_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
     bool evk_valid = false;
     LocusDev L;
+    LocusDev* d_L = nullptr;        // device copy (the slow path of the register kernel reads it by pointer)
     int U = 0, kb = 3, sm_count = 148;
     int n_raw[2] = {0, 0};
     double K = 0, gamma = 0, p = 0;
@@ -419,6 +420,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->h_res.resize(3 + (size_t)5 * U);
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
     CU(cudaMemsetAsync(acc.counters, 0, 2 * sizeof(u64), e->stream));
+    if ((rc = dev_upload(e, &e->d_L, &e->L, 1))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
@@ -487,13 +489,13 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
             bool done = false;
             const bool dominant = j == jdom;
             if (dominant) CU(cudaEventRecord(e->evk0, e->stream));
-            if (e->use_reg_kernel && (rc = exhaustive_launch(e->L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh)))
+            if (e->use_reg_kernel && (rc = exhaustive_launch(e->L, e->d_L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh)))
                 return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             if (!done) {
                 size_t smem = 0;
                 const int wk = std::max(j, 1);
                 if ((rc = ensure_score_smem(e, wk, &smem))) return rc;
-                const int chunk = 16;
+                const int chunk = (re - rb) >= (u64)e->sm_count * SCORE_WARPS * 64 ? 16 : 1;
                 const u64 nchunks = (re - rb + chunk - 1) / chunk;
                 const int blocks = (int)std::min<u64>((nchunks + SCORE_WARPS - 1) / SCORE_WARPS, (u64)e->sm_count * 8);
                 exhaustive_generic_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, j, rb, re, chunk, wk);

@@ -1,0 +1,494 @@
+// Register kernel of the exhaustive path: one LANE per union subset (pair / triple), FP64 in registers.
+//
+// Replaces the OpenMP loop of PostCal::computeTotalLikelihood (postcal.cpp:769-1044) for the subset-size
+// classes j = 2 and j = 3 (the reference's exhaustive limit, postcal.cpp:760-762).  For a triple (a < b < x)
+// of internal union SNPs:
+//   * a and b are WARP-UNIFORM (a fixed per work item, b walks a window of up to 32 consecutive SNPs),
+//     x is the LANE's SNP (a 32-wide tile): LD rows a and b are read coalesced, everything that depends on
+//     (a), (a,b) or (a,x) only is computed once per item / window / tile and reused;
+//   * per study the kernel needs E_s(C) = exp(f_s(C)) for the 8 sub-masks of {a,b,x}; 6 of them are loop
+//     invariant, the other two ({b,x} and {a,b,x}) cost one bordered Cholesky step + rsqrt + exp each;
+//   * the <= 27 expansions (postcal.cpp:903-958) are products E_0[m0] E_1[m1], summed per (SNP, state) cell.
+//
+// Two numeric regimes (DESIGN.md "range"):
+//   FAST  every E_s(mask) of the triple is below 2^450: all E's are ordinary doubles, every cell is a plain
+//         double sum, accumulators are plain doubles in lane registers (x cells per tile, a cells per item) or
+//         in the per-warp shared-memory window (b cells, after a shuffle reduction).  No exponent bookkeeping.
+//   SLOW  otherwise (a very strongly associated SNP is involved): the lane re-evaluates the triple with
+//         mantissa/exponent arithmetic, sums each cell relative to its structurally largest term and adds
+//         the results straight to the binned store.  Per-lane, divergent, rare.
+// Both regimes leave the SM as native fp64 atomic adds into the exponent-binned accumulator store (common.cuh).
+//
+// Work decomposition: item = (a, b-window, chunk of x tiles), handed out by an atomic counter; the union-
+// subset rank range [r_begin, r_end) of the C-ABI is honoured by a lexicographic predicate per lane.
+#pragma once
+#include "common.cuh"
+
+namespace pipsort {
+
+typedef unsigned long long u64;
+
+constexpr int EXH_WARPS = 4;          // warps per block
+constexpr int EXH_BW = 32;            // max b-window
+constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
+constexpr double FAST_LIMIT = 0x1p+450;
+
+struct E2 { double m; int n; };       // m * 2^n, m a positive normal double
+
+// m * 2^e for a positive normal m; 0 when the result would leave the normal range downwards
+__device__ __forceinline__ double scale2(double m, int e) {
+    e = max(min(e, 900), -2040);
+    const int hi = __double2hiint(m);
+    const int f = (hi >> 20) + e;
+    const double r = __hiloint2double(hi + (e << 20), __double2loint(m));
+    return f > 0 ? r : 0.0;
+}
+
+// exp(t) for t >= 0 as an ordinary double; +inf-like huge values when t is beyond the double range
+__device__ __forceinline__ double exp_pos(double t) {
+    double m;
+    int n;
+    xexp(t, m, n);
+    n = min(n, 1000);
+    return __hiloint2double(__double2hiint(m) + (n << 20), __double2loint(m));
+}
+
+// E{C + y} = E{C} * exp(hd r^2 / s) / sqrt(s)   (bordered Cholesky step: s = Schur complement, r = residual)
+__device__ __forceinline__ E2 extend(const E2& base, double hd, double r, double s, int& bad) {
+    bad |= !(s > 0.25);                          // A >= I  =>  every Schur complement is >= 1 (postcal.cpp:291-294)
+    const double rs = rsqrt(s);
+    const double u = r * rs;
+    double em;
+    int en;
+    xexp(hd * (u * u), em, en);
+    return E2{base.m * (em * rs), base.n + en};
+}
+__device__ __forceinline__ double extend_fast(double base, double hd, double r, double s, int& bad) {
+    bad |= !(s > 0.25);
+    const double rs = rsqrt(s);
+    const double u = r * rs;
+    return base * (exp_pos(hd * (u * u)) * rs);
+}
+
+constexpr __host__ __device__ bool in0(int t) { return t != 1; }   // state 0: study 0 only, 1: study 1 only, 2: both
+constexpr __host__ __device__ bool in1(int t) { return t != 0; }
+
+struct ExhParams {
+    int J;                 // 2 or 3
+    int bw;                // b-window size (<= 32)
+    int xch;               // x tiles per item
+    u64 r_begin, r_end;    // in-class rank range (lexicographic over internal order)
+    int a_lo, a_hi;        // J == 3: range of a that intersects the rank range
+    const u64* item_prefix;  // [a_hi - a_lo + 2] cumulative number of items (J == 3), or [2] for J == 2
+    u64 n_items;
+    unsigned* counter;     // work-queue head
+    int lo[3], hi[3];      // lexicographic bounds of the rank range: first subset in range, first subset past it
+    bool partial;          // false: the whole class is in range (no per-lane predicate)
+};
+
+template <int J>
+__device__ __forceinline__ bool lex_in_range(const ExhParams& P, int a, int b, int x) {
+    if (J == 3) {
+        const bool ge = (a > P.lo[0]) || (a == P.lo[0] && (b > P.lo[1] || (b == P.lo[1] && x >= P.lo[2])));
+        const bool lt = (a < P.hi[0]) || (a == P.hi[0] && (b < P.hi[1] || (b == P.hi[1] && x < P.hi[2])));
+        return ge && lt;
+    } else {
+        const bool ge = (b > P.lo[0]) || (b == P.lo[0] && x >= P.lo[1]);
+        const bool lt = (b < P.hi[0]) || (b == P.hi[0] && x < P.hi[1]);
+        return ge && lt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SLOW path: one subset, one lane, mantissa/exponent arithmetic, results straight to the bins.
+// ---------------------------------------------------------------------------------------------------------
+template <int J>
+__device__ __noinline__ void slow_subset(const LocusDev& L, int a, int b, int x) {
+    constexpr bool HAS_A = (J == 3);
+    constexpr int FULL = HAS_A ? 7 : 6;
+    const AccDev& acc = L.acc;
+    int bad = 0;
+    E2 E[2][8];
+    int pen[2][3];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const StudyDev& S = L.st[s];
+        const int la = HAS_A ? L.loc[s][a] : -1, lb = L.loc[s][b], lx = L.loc[s][x];
+        const bool ha = la >= 0, hb = lb >= 0, hx = lx >= 0;
+        pen[s][0] = (!HAS_A || ha) ? 0 : PEN; pen[s][1] = hb ? 0 : PEN; pen[s][2] = hx ? 0 : PEN;
+        // virtual SNPs: A = 1, z = 0, W = 0  ->  E unchanged
+        const double Aa = ha ? S.A[la] : 1.0, za = ha ? S.z[la] : 0.0;
+        const double Ab = hb ? S.A[lb] : 1.0, zb = hb ? S.z[lb] : 0.0;
+        const double Ax = hx ? S.A[lx] : 1.0, zx = hx ? S.z[lx] : 0.0;
+        const double Wab = (ha && hb) ? S.W[(size_t)la * S.ldw + lb] : 0.0;
+        const double Wax = (ha && hx) ? S.W[(size_t)la * S.ldw + lx] : 0.0;
+        const double Wbx = (hb && hx) ? S.W[(size_t)lb * S.ldw + lx] : 0.0;
+        const E2 one{1.0, 0};
+        E[s][0] = one;
+        E[s][1] = ha ? E2{S.e1m[la], S.e1n[la]} : one;
+        E[s][2] = hb ? E2{S.e1m[lb], S.e1n[lb]} : one;
+        E[s][4] = hx ? E2{S.e1m[lx], S.e1n[lx]} : one;
+        const double iAa = 1.0 / Aa, iAb = 1.0 / Ab;
+        const double s22 = fma(-Wab * Wab, iAa, Ab), r2 = fma(-Wab * za, iAa, zb);
+        E[s][3] = extend(E[s][1], S.hd, r2, s22, bad);
+        const double cx = fma(-Wax * Wax, iAa, Ax), rx = fma(-Wax * za, iAa, zx);
+        E[s][5] = extend(E[s][1], S.hd, rx, cx, bad);
+        const double s6 = fma(-Wbx * Wbx, iAb, Ax), r6 = fma(-Wbx * zb, iAb, zx);
+        E[s][6] = extend(E[s][2], S.hd, r6, s6, bad);
+        const double i22 = 1.0 / s22;
+        const double tt = fma(-Wab * Wax, iAa, Wbx);
+        const double s7 = fma(-tt * tt, i22, cx), r7 = fma(-tt * r2, i22, rx);
+        E[s][7] = extend(E[s][3], S.hd, r7, s7, bad);
+    }
+    if (bad) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+    // numerator exponents carry the penalties of the SNPs the study lacks; reference exponents do not
+    auto fam = [&](int s, int m, int ref) -> double {
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) if (m >> i & 1) p += pen[s][i];
+        return scale2(E[s][m].m, E[s][m].n + p - E[s][ref].n);
+    };
+    const int snp[3] = {a, b, x};
+    XAcc tot = xacc_empty();
+#pragma unroll
+    for (int i = HAS_A ? 0 : 1; i < 3; i++) {
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int bit = 1 << i;
+            const int r0 = in0(t) ? FULL : FULL ^ bit, r1 = in1(t) ? FULL : FULL ^ bit;
+            double g[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < (HAS_A ? 9 : 3); q++) {   // states of the other SNPs
+                int st[3];
+                st[i] = t;
+                int qq = q;
+#pragma unroll
+                for (int k = HAS_A ? 0 : 1; k < 3; k++) if (k != i) { st[k] = qq % 3; qq /= 3; }
+                int m0 = 0, m1 = 0, ac = 0;
+#pragma unroll
+                for (int k = HAS_A ? 0 : 1; k < 3; k++) {
+                    if (in0(st[k])) m0 |= 1 << k;
+                    if (in1(st[k])) m1 |= 1 << k;
+                    if (k != i && st[k] == 2) ac++;
+                }
+                g[ac] = fma(fam(0, m0, r0), fam(1, m1, r1), g[ac]);
+            }
+            const int nref = E[0][r0].n + E[1][r1].n;
+            const double pa = L.pi[J][t == 2 ? 1 : 0], pb = L.pi[J][t == 2 ? 2 : 1], pc = (HAS_A ? L.pi[J][t == 2 ? 3 : 2] : 0.0);
+            const double xv = fma(g[0], pa, fma(g[1], pb, g[2] * pc));
+            const double yv = g[0] + g[1] + g[2];
+            bin_add(acc, t == 0 ? X1 : (t == 1 ? X2 : X3), snp[i], xv, nref);
+            bin_add(acc, t == 2 ? YS : YN, snp[i], yv, nref);
+            if (i == 2) xadd(tot, xv, nref);
+        }
+    }
+    bin_add(acc, SCAL, S_TOTAL, tot);
+    {   // no causal SNP in study 1 / study 0  (postcal.cpp:988-1000)
+        int p0 = 0, p1 = 0;
+#pragma unroll
+        for (int i = HAS_A ? 0 : 1; i < 3; i++) { p0 += pen[0][i]; p1 += pen[1][i]; }
+        if (p0 == 0) bin_add(acc, SCAL, S_NC1, L.pi[J][0] * E[0][FULL].m, E[0][FULL].n);
+        if (p1 == 0) bin_add(acc, SCAL, S_NC0, L.pi[J][0] * E[1][FULL].m, E[1][FULL].n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-warp shared-memory window: everything that depends on (a, b) or on b alone, for <= 32 values of b
+// ---------------------------------------------------------------------------------------------------------
+struct WinStudy {
+    double Wab[EXH_BW];    // d Sigma[a][b]                      (0 when a or b is absent from the study)
+    double inv22[EXH_BW];  // 1 / Schur(b | a)
+    double c2[EXH_BW];     // residual(b | a) / Schur(b | a)
+    double invAb[EXH_BW];  // 1 / A_b
+    double ub[EXH_BW];     // z_b / A_b
+    double v2[EXH_BW];     // E{b}   (0 when b is absent from the study)
+    double v3[EXH_BW];     // E{a,b} (0 when a or b is absent)
+    int locb[EXH_BW];      // study-local index of b or -1
+};
+struct WarpWin {
+    WinStudy st[2];
+    double acc[EXH_BW][5];   // b-cell accumulators of the window, flushed at the end of the item
+    int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
+};
+
+template <int J>
+__global__ void __launch_bounds__(EXH_WARPS * 32, 3)
+exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) {
+    constexpr bool HAS_A = (J == 3);
+    __shared__ WarpWin wins[EXH_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpWin& win = wins[wib];
+    const AccDev& acc = L.acc;
+    const int U = L.U;
+    const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
+
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(P.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((u64)item >= P.n_items) break;
+
+        // ---- decode the item: a, first b of the window, first x tile, number of x tiles ---------------
+        int a = -1, b0, nb, xt0, nxt;
+        {
+            u64 rem = item;
+            if (HAS_A) {
+                int lo = 0, hi = P.a_hi - P.a_lo;            // largest i with prefix[i] <= item
+                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.item_prefix[mid] <= (u64)item) lo = mid; else hi = mid - 1; }
+                a = P.a_lo + lo;
+                rem = item - P.item_prefix[lo];
+            }
+            const int bfirst = a + 1, blast = U - 2;         // b in [bfirst, blast], x in (b, U-1]
+            int w = 0;
+            for (;; w++) {                                   // windows of this a, each split into x-tile chunks
+                const int wb0 = bfirst + w * P.bw;
+                const int t0 = (wb0 + 1) >> 5, t1 = (U - 1) >> 5;
+                const u64 chunks = (u64)((t1 - t0 + 1 + P.xch - 1) / P.xch);
+                if (rem < chunks) { b0 = wb0; xt0 = t0 + (int)rem * P.xch; nxt = min(P.xch, t1 - xt0 + 1); break; }
+                rem -= chunks;
+            }
+            nb = min(P.bw, blast - b0 + 1);
+        }
+
+        // ---- per-item uniform values of a ---------------------------------------------------------------
+        int ha[2] = {0, 0}, la[2] = {-1, -1};
+        double invAa[2] = {1.0, 1.0}, ua[2] = {0.0, 0.0}, v1[2] = {0.0, 0.0};
+        bool okA = true;
+        int bad = 0;
+        if (HAS_A) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                la[s] = L.loc[s][a];
+                ha[s] = la[s] >= 0;
+                if (ha[s]) {
+                    invAa[s] = L.st[s].invA[la[s]];
+                    ua[s] = L.st[s].u[la[s]];
+                    const int n = L.st[s].e1n[la[s]];
+                    okA = okA && n < 440;
+                    v1[s] = scale2(L.st[s].e1m[la[s]], min(n, 900));
+                }
+            }
+        }
+        if (!okA) { v1[0] = 0.0; v1[1] = 0.0; }             // every subset of this item takes the slow path
+        const int nstates_a = HAS_A ? (ha[0] && ha[1] ? 3 : (ha[0] || ha[1] ? 1 : 0)) : 1;
+
+        // ---- window table: lane t prepares b = b0 + t -----------------------------------------------------
+        __syncwarp();
+        {
+            const int b = b0 + lane;
+            const bool bv = lane < nb;
+            int okb = 1;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const StudyDev& S = L.st[s];
+                WinStudy& w = win.st[s];
+                const int lb = bv ? L.loc[s][b] : -1;
+                const bool hb = lb >= 0;
+                double Wab = 0.0, invAb = 1.0, ub = 0.0, Ab = 1.0, zb = 0.0, v2 = 0.0, v3 = 0.0;
+                if (hb) {
+                    invAb = S.invA[lb]; ub = S.u[lb]; Ab = S.A[lb]; zb = S.z[lb];
+                    const int n = S.e1n[lb];
+                    okb &= n < 440;
+                    v2 = scale2(S.e1m[lb], min(n, 900));
+                    if (HAS_A && ha[s]) Wab = S.W[(size_t)la[s] * S.ldw + lb];
+                }
+                // bordered step a -> {a,b}:  Schur = A_b - W_ab^2 / A_a,  residual = z_b - W_ab z_a / A_a
+                const double s22 = fma(-Wab * Wab, invAa[s], Ab);
+                const double r2 = fma(-Wab, ua[s], zb);
+                const double inv22 = 1.0 / s22;
+                if (HAS_A && ha[s] && hb) {
+                    v3 = extend_fast(v1[s], S.hd, r2, s22, bad);
+                    okb &= v3 < FAST_LIMIT;
+                }
+                w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = r2 * inv22;
+                w.invAb[lane] = invAb; w.ub[lane] = ub;
+                w.v2[lane] = v2; w.v3[lane] = v3;
+                w.locb[lane] = lb;
+            }
+            if (!okb) { win.st[0].v2[lane] = 0.0; win.st[0].v3[lane] = 0.0; win.st[1].v2[lane] = 0.0; win.st[1].v3[lane] = 0.0; }
+            win.ok[lane] = okb;
+#pragma unroll
+            for (int k = 0; k < 5; k++) win.acc[lane][k] = 0.0;
+        }
+        __syncwarp();
+
+        // ---- item-lifetime accumulators (lane private, plain doubles) ------------------------------------------
+        double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+        unsigned nconf = 0;
+
+        for (int xt = xt0; xt < xt0 + nxt; xt++) {
+            const int x = xt * 32 + lane;
+            const bool xin = x < U;
+            // ---- per-tile lane values of x: masks {x} (4) and {a,x} (5) ----------------------------------
+            int hx[2], lx[2];
+            double px[2], cx[2], rx[2], Ax[2], zx[2], v4[2], v5[2];
+            bool okX = true;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const StudyDev& S = L.st[s];
+                lx[s] = xin ? L.loc[s][x] : -1;
+                hx[s] = lx[s] >= 0;
+                double Wax = 0.0;
+                Ax[s] = 1.0; zx[s] = 0.0; v4[s] = 0.0; v5[s] = 0.0;
+                if (hx[s]) {
+                    Ax[s] = S.A[lx[s]]; zx[s] = S.z[lx[s]];
+                    const int n = S.e1n[lx[s]];
+                    okX = okX && n < 440;
+                    v4[s] = scale2(S.e1m[lx[s]], min(n, 900));
+                    if (HAS_A && ha[s]) Wax = S.W[(size_t)la[s] * S.ldw + lx[s]];
+                }
+                px[s] = Wax * invAa[s];
+                cx[s] = fma(-Wax, px[s], Ax[s]);
+                rx[s] = fma(-Wax, ua[s], zx[s]);
+                if (HAS_A && ha[s] && hx[s]) {
+                    v5[s] = extend_fast(v1[s], S.hd, rx[s], cx[s], bad);
+                    okX = okX && v5[s] < FAST_LIMIT;
+                }
+            }
+            okX = okX && okA;
+            if (!okX) { v4[0] = 0.0; v4[1] = 0.0; v5[0] = 0.0; v5[1] = 0.0; }
+            const int nstates_x = hx[0] && hx[1] ? 3 : (hx[0] || hx[1] ? 1 : 0);
+            double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            const bool diag = P.partial || (b0 + nb - 1 >= xt * 32);     // some lane may be inactive at some step
+
+            for (int t = 0; t < nb; t++) {
+                const int b = b0 + t;
+                if (b >= xt * 32 + 31) break;                       // no x of this tile is beyond b
+                bool active = xin;
+                if (diag) {
+                    active = active && x > b;
+                    if (P.partial) active = active && lex_in_range<J>(P, a, b, x);
+                }
+                double v[2][8];
+                int hb[2];
+                bool ok = okX && win.ok[t];
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const StudyDev& S = L.st[s];
+                    const WinStudy& w = win.st[s];
+                    const int lb = w.locb[t];
+                    hb[s] = lb >= 0;
+                    double e6 = 0.0, e7 = 0.0;
+                    if (hb[s] && hx[s]) {
+                        const double Wbx = S.W[(size_t)lb * S.ldw + lx[s]];
+                        const double s6 = fma(-Wbx * Wbx, w.invAb[t], Ax[s]);
+                        const double r6 = fma(-Wbx, w.ub[t], zx[s]);
+                        e6 = extend_fast(w.v2[t], S.hd, r6, s6, bad);
+                        if (HAS_A && ha[s]) {
+                            const double tt = fma(-w.Wab[t], px[s], Wbx);
+                            const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
+                            const double r7 = fma(-tt, w.c2[t], rx[s]);
+                            e7 = extend_fast(w.v3[t], S.hd, r7, s7, bad);
+                        }
+                    }
+                    ok = ok && (e6 < FAST_LIMIT) && (e7 < FAST_LIMIT);
+                    v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
+                    v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6; v[s][7] = e7;
+                }
+                const int nstates_b = hb[0] && hb[1] ? 3 : (hb[0] || hb[1] ? 1 : 0);
+                if (active) nconf += (unsigned)(nstates_a * nstates_b * nstates_x);
+                if (active && !ok) slow_subset<J>(*Lg, a, b, x);      // rare, divergent, self-contained
+                if (!(active && ok)) {                              // this lane contributes nothing on the fast path
+#pragma unroll
+                    for (int s = 0; s < 2; s++) { v[s][4] = 0.0; v[s][5] = 0.0; v[s][6] = 0.0; v[s][7] = 0.0; }
+                }
+
+                // ---- cells: G[snp][state][a'] = sum over the expansions with that SNP in that state ----------
+                // snp 0 = a, 1 = b, 2 = x ; a' = number of OTHER SNPs causal in both studies
+                double G[3][3][3];
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+#pragma unroll
+                        for (int r = 0; r < 3; r++) G[i][q][r] = 0.0;
+#pragma unroll
+                for (int tx = 0; tx < 3; tx++)
+#pragma unroll
+                    for (int tb = 0; tb < 3; tb++)
+#pragma unroll
+                        for (int ta = 0; ta < (HAS_A ? 3 : 1); ta++) {
+                            const int m0 = (HAS_A && in0(ta) ? 1 : 0) | (in0(tb) ? 2 : 0) | (in0(tx) ? 4 : 0);
+                            const int m1 = (HAS_A && in1(ta) ? 1 : 0) | (in1(tb) ? 2 : 0) | (in1(tx) ? 4 : 0);
+                            const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
+                            G[2][tx][ac - (tx == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[2][tx][ac - (tx == 2 ? 1 : 0)]);
+                            G[1][tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[1][tb][ac - (tb == 2 ? 1 : 0)]);
+                            if (HAS_A) G[0][ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[0][ta][ac - (ta == 2 ? 1 : 0)]);
+                        }
+                auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
+                    return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
+                };
+                auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
+                {
+                    const double x1 = wsumX(G[2][0], false), x2 = wsumX(G[2][1], false), x3 = wsumX(G[2][2], true);
+                    accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
+                    accX[YS] += sumY(G[2][2]);
+                    accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
+                    accT += (x1 + x2) + x3;                                        // every expansion exactly once
+                }
+                if (HAS_A) {
+                    accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
+                    accA[YS] += sumY(G[0][2]);
+                    accA[YN] += sumY(G[0][0]) + sumY(G[0][1]);
+                }
+                // no causal SNP in study 1 (0): every chosen SNP causal in study 0 (1) only  (postcal.cpp:988-1000)
+                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
+                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+                {   // b cells -> shuffle reduction -> shared-memory window accumulators
+                    double vb[5];
+                    vb[X1] = wsumX(G[1][0], false); vb[X2] = wsumX(G[1][1], false); vb[X3] = wsumX(G[1][2], true);
+                    vb[YS] = sumY(G[1][2]);
+                    vb[YN] = sumY(G[1][0]) + sumY(G[1][1]);
+                    double mine = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        double r = vb[k];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                        if (lane == k) mine = r;
+                    }
+                    if (lane < 5) win.acc[t][lane] += mine;
+                }
+            }  // b window
+
+            if (xin) {   // flush the x cells of this tile
+#pragma unroll
+                for (int k = 0; k < 5; k++) bin_add(acc, k, x, accX[k], 0);
+            }
+        }  // x tiles
+
+        // ---- flush the item: b window, a cells, scalars -----------------------------------------------------
+        __syncwarp();
+        if (lane < nb) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) bin_add(acc, k, b0 + lane, win.acc[lane][k], 0);
+        }
+        {
+            double r[8];
+#pragma unroll
+            for (int k = 0; k < 5; k++) r[k] = accA[k];
+            r[5] = accT; r[6] = accNC0; r[7] = accNC1;
+            unsigned cnt = nconf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = HAS_A ? 0 : 5; k < 8; k++) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            }
+            if (lane == 0) {
+                if (HAS_A) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) bin_add(acc, k, a, r[k], 0);
+                }
+                bin_add(acc, SCAL, S_TOTAL, r[5], 0);
+                bin_add(acc, SCAL, S_NC0, r[6], 0);
+                bin_add(acc, SCAL, S_NC1, r[7], 0);
+                atomicAdd(acc.counters, (u64)cnt);
+            }
+            if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace pipsort
