@@ -8,7 +8,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-LIB = os.path.join(LIBDIR, "libpipsort_b200.so")
+LIB = os.environ.get("PIPSORT_B200_LIB") or os.path.join(LIBDIR, "libpipsort_b200.so")
 HOST_BIN = os.path.join(LIBDIR, "PIPSORT")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",

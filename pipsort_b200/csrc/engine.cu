@@ -82,21 +82,21 @@ __global__ void study_vectors_kernel(const double* __restrict__ W, int ldw, cons
 }
 
 // ---- finalize: bins -> log-space results --------------------------------------------------------------
-__device__ inline XAcc bins_read(const AccDev& a, int slot, int g) {
+// warp-collective: lanes scan the bins of one accumulator in parallel, the top three non-empty bins give M 2^N
+__device__ inline XAcc bins_read_warp(const AccDev& a, int slot, int g, int lane) {
     const double* p = bin_ptr(a, slot, g);
-    for (int b = a.NB - 1; b >= 0; b--) {
-        const double v = p[(size_t)b * a.Upad];
-        if (v > 0.0) {
-            double M = v;
-            if (b > 0) M += p[(size_t)(b - 1) * a.Upad] * 0x1p-512;
-            if (b > 1) M += (p[(size_t)(b - 2) * a.Upad] * 0x1p-512) * 0x1p-512;
-            int hi = __double2hiint(M);
-            int e = ((hi >> 20) & 0x7ff) - 1023;
-            M = __hiloint2double(hi - (e << 20), __double2loint(M));
-            return XAcc{M, 512 * b - a.bias + e};
-        }
-    }
-    return xacc_empty();
+    int top = -1;
+    for (int b = lane; b < a.NB; b += 32)
+        if (p[(size_t)b * a.Upad] > 0.0) top = b;
+    top = __reduce_max_sync(0xffffffffu, top);
+    if (top < 0) return xacc_empty();
+    double M = p[(size_t)top * a.Upad];
+    if (top > 0) M += p[(size_t)(top - 1) * a.Upad] * 0x1p-512;
+    if (top > 1) M += (p[(size_t)(top - 2) * a.Upad] * 0x1p-512) * 0x1p-512;
+    const int hi = __double2hiint(M);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    M = __hiloint2double(hi - (e << 20), __double2loint(M));
+    return XAcc{M, 512 * top - a.bias + e};
 }
 
 // log(M 2^N) + c ; 0.0 (the reference's "empty" sentinel, postcal.h:102-112) when nothing was added
@@ -109,11 +109,21 @@ __device__ inline double xlog_or_zero(const XAcc& a, double c) {
 
 // res: [0] total, [1] noCausal[0], [2] noCausal[1], then 5 arrays of U (internal order):
 //      postValues study 0, postValues study 1, sharedPips, sharedLL, notSharedLL
-__global__ void finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < 3) res[g] = xlog_or_zero(bins_read(acc, SCAL, g), cx);
+// One warp per union SNP (plus one warp per scalar).
+constexpr int FIN_WARPS = 8;
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    if (w < 3) {
+        const XAcc v = bins_read_warp(acc, SCAL, w, lane);
+        if (lane == 0) res[w] = xlog_or_zero(v, cx);
+        return;
+    }
+    const int g = w - 3;
     if (g >= U) return;
-    XAcc x1 = bins_read(acc, X1, g), x2 = bins_read(acc, X2, g), x3 = bins_read(acc, X3, g);
+    const XAcc x1 = bins_read_warp(acc, X1, g, lane), x2 = bins_read_warp(acc, X2, g, lane), x3 = bins_read_warp(acc, X3, g, lane);
+    const XAcc ys = bins_read_warp(acc, YS, g, lane), yn = bins_read_warp(acc, YN, g, lane);
+    if (lane != 0) return;
     XAcc p0 = x1, p1 = x2;
     xmerge(p0, x3);
     xmerge(p1, x3);
@@ -121,8 +131,8 @@ __global__ void finalize_kernel(AccDev acc, int U, double cx, double cy, double*
     r[g] = xlog_or_zero(p0, cx);
     r[U + g] = xlog_or_zero(p1, cx);
     r[2 * U + g] = xlog_or_zero(x3, cx);
-    r[3 * U + g] = xlog_or_zero(bins_read(acc, YS, g), cy);
-    r[4 * U + g] = xlog_or_zero(bins_read(acc, YN, g), cy);
+    r[3 * U + g] = xlog_or_zero(ys, cy);
+    r[4 * U + g] = xlog_or_zero(yn, cy);
 }
 
 __global__ void add_bins_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
@@ -480,28 +490,31 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
             o += cnt;
         }
     }
+    // size classes 0..3: one launch of the register kernel (exhaustive.cuh); larger classes: generic kernel
+    const int jreg = e->use_reg_kernel ? std::min(std::min(c, 3), e->U) : -1;
+    if (jreg >= 0) {
+        if (jdom <= jreg) CU(cudaEventRecord(e->evk0, e->stream));
+        if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh)))
+            return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        if (jdom <= jreg) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
+    }
     u64 off = 0;
     for (int j = 0; j <= std::min(c, e->U); j++) {
         const u64 cnt = binom_host(e->U, j, nullptr);
         const u64 lo = std::max<u64>(rank_begin, off), hi = std::min<u64>(rank_end, off + cnt);
-        if (lo < hi) {
+        if (lo < hi && j > jreg) {
             const u64 rb = lo - off, re = hi - off;
-            bool done = false;
             const bool dominant = j == jdom;
             if (dominant) CU(cudaEventRecord(e->evk0, e->stream));
-            if (e->use_reg_kernel && (rc = exhaustive_launch(e->L, e->d_L, j, rb, re, e->sm_count, e->stream, &done, &e->launches, &e->exh)))
-                return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-            if (!done) {
-                size_t smem = 0;
-                const int wk = std::max(j, 1);
-                if ((rc = ensure_score_smem(e, wk, &smem))) return rc;
-                const int chunk = (re - rb) >= (u64)e->sm_count * SCORE_WARPS * 64 ? 16 : 1;
-                const u64 nchunks = (re - rb + chunk - 1) / chunk;
-                const int blocks = (int)std::min<u64>((nchunks + SCORE_WARPS - 1) / SCORE_WARPS, (u64)e->sm_count * 8);
-                exhaustive_generic_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, j, rb, re, chunk, wk);
-                e->launches++;
-                CU(cudaGetLastError());
-            }
+            size_t smem = 0;
+            const int wk = std::max(j, 1);
+            if ((rc = ensure_score_smem(e, wk, &smem))) return rc;
+            const int chunk = (re - rb) >= (u64)e->sm_count * SCORE_WARPS * 64 ? 16 : 1;
+            const u64 nchunks = (re - rb + chunk - 1) / chunk;
+            const int blocks = (int)std::min<u64>((nchunks + SCORE_WARPS - 1) / SCORE_WARPS, (u64)e->sm_count * 8);
+            exhaustive_generic_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, j, rb, re, chunk, wk);
+            e->launches++;
+            CU(cudaGetLastError());
             if (dominant) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
         }
         off += cnt;
@@ -560,7 +573,7 @@ int pipsort_finalize(pipsort_engine* e) {
     CU(cudaSetDevice(e->device));
     const int U = e->U;
     const double cy = -0.5 * e->K, cx = cy + U * std::log(1.0 - e->gamma);
-    finalize_kernel<<<(std::max(U, 3) + 127) / 128, 128, 0, e->stream>>>(e->L.acc, U, cx, cy, e->d_res);
+    finalize_kernel<<<(U + 3 + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, e->stream>>>(e->L.acc, U, cx, cy, e->d_res);
     e->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -15,7 +15,9 @@ struct ExhScratch {           // owned by the engine, reused across launches
     u64* d_prefix = nullptr;
     size_t cap_prefix = 0;
     unsigned* d_counter = nullptr;
-    int occ2 = 0, occ3 = 0;   // resident blocks per SM of the two instantiations
+    int occ = 0;              // resident blocks per SM of exhaustive_all_kernel
+    // key of the prefix table currently on the device
+    int k_U = -1, k_bw = 0, k_xch = 0, k_alo = 0, k_ahi = 0;
 };
 
 inline u64 exh_binom(int n, int k) {
@@ -52,71 +54,99 @@ inline u64 exh_items_of(int U, int a, int bw, int xch) {
     return n;
 }
 
-// Launches the register kernel for the in-class rank range [rb, re) of size class j.  *done = false when the
-// class is not covered (j not in {2,3} or a degenerate locus) and the caller must use the generic kernel.
-// Returns a cudaError_t as int.
-inline int exhaustive_launch(const LocusDev& L, const LocusDev* Lg, int j, u64 rb, u64 re, int sm_count, cudaStream_t stream, bool* done,
-                             unsigned long long* launches, ExhScratch* sc) {
-    *done = false;
-    const int U = L.U;
-    if ((j != 2 && j != 3) || U < j || rb >= re) return 0;
-    cudaError_t err;
-    if (!sc->d_counter) {
-        if ((err = cudaMalloc(&sc->d_counter, sizeof(unsigned))) != cudaSuccess) return (int)err;
-        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ2, exhaustive_reg_kernel<2>, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
-        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ3, exhaustive_reg_kernel<3>, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
-    }
-    ExhParams P;
+// Fills the rank-range part of P for size class j; returns false when the class does not intersect.
+inline bool exh_class_params(ExhParams& P, int U, int j, u64 rb, u64 re) {
     memset(&P, 0, sizeof P);
     P.J = j;
-    P.r_begin = rb; P.r_end = re;
+    if (U < j || rb >= re) return false;
     const u64 total = exh_binom(U, j);
+    P.r_begin = rb; P.r_end = re;
     P.partial = !(rb == 0 && re == total);
     int glo[3] = {0, 0, 0}, ghi[3] = {U, U, U};
     exh_unrank(rb, U, j, glo);
     if (re < total) exh_unrank(re, U, j, ghi);
     for (int i = 0; i < 3; i++) { P.lo[i] = glo[i]; P.hi[i] = ghi[i]; }
-    const int occ = std::max(1, j == 3 ? sc->occ3 : sc->occ2);
+    if (j == 3) {
+        P.a_lo = glo[0];
+        P.a_hi = std::min(re < total ? ghi[0] : U - 3, U - 3);
+    } else {
+        P.a_lo = P.a_hi = -1;
+    }
+    return true;
+}
+
+// Launches ONE kernel for the size classes 0..min(c,3) restricted to the global union-subset rank range
+// [rank_begin, rank_end) (size-then-lexicographic order over the internal SNP order).  Returns a cudaError_t.
+inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u64 rank_begin, u64 rank_end, int sm_count,
+                                 cudaStream_t stream, unsigned long long* launches, ExhScratch* sc) {
+    const int U = L.U;
+    cudaError_t err;
+    if (!sc->d_counter) {
+        if ((err = cudaMalloc(&sc->d_counter, sizeof(unsigned))) != cudaSuccess) return (int)err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
+    }
+    ExhAll A;
+    memset(&A, 0, sizeof A);
+    u64 off = 0;
+    bool have3 = false, have2 = false;
+    for (int j = 0; j <= std::min(std::min(c, 3), U); j++) {
+        const u64 cnt = exh_binom(U, j);
+        const u64 lo = std::max<u64>(rank_begin, off), hi = std::min<u64>(rank_end, off + cnt);
+        if (lo < hi) {
+            const u64 rb = lo - off, re = hi - off;
+            if (j == 0) A.do_null = 1;
+            else if (j == 1) { A.x1_lo = (int)rb; A.x1_hi = (int)re; A.tile1_0 = A.x1_lo >> 5; A.n1_tiles = ((A.x1_hi - 1) >> 5) - A.tile1_0 + 1; }
+            else if (j == 2) have2 = exh_class_params(A.p2, U, 2, rb, re);
+            else have3 = exh_class_params(A.p3, U, 3, rb, re);
+        }
+        off += cnt;
+    }
+    const int occ = std::max(1, sc->occ);
     const u64 slots = (u64)sm_count * occ * EXH_WARPS;
     // granularity: large items amortise the per-item setup, but there must be enough of them to balance
     const int cand[][2] = {{32, 1 << 20}, {32, 16}, {32, 8}, {32, 4}, {32, 2}, {32, 1}, {16, 1}, {8, 1}};
     std::vector<u64> prefix;
-    u64 n_items = 0;
-    for (const auto& cd : cand) {
-        P.bw = cd[0]; P.xch = cd[1];
-        prefix.clear();
-        if (j == 3) {
-            P.a_lo = glo[0];
-            P.a_hi = std::min(re < total ? ghi[0] : U - 3, U - 3);
+    if (have3) {
+        ExhParams& P = A.p3;
+        for (const auto& cd : cand) {
+            P.bw = cd[0]; P.xch = cd[1];
+            u64 n = 0;
+            for (int a = P.a_lo; a <= P.a_hi; a++) n += exh_items_of(U, a, P.bw, P.xch);
+            A.n3 = n;
+            if (n >= 6 * slots) break;
+        }
+        if (A.n3 >= 0xfff00000ull) return (int)cudaErrorInvalidValue;   // 32-bit work queue (never in practice)
+        if (!(sc->k_U == U && sc->k_bw == P.bw && sc->k_xch == P.xch && sc->k_alo == P.a_lo && sc->k_ahi == P.a_hi)) {
             prefix.push_back(0);
             for (int a = P.a_lo; a <= P.a_hi; a++) prefix.push_back(prefix.back() + exh_items_of(U, a, P.bw, P.xch));
-            n_items = prefix.back();
-        } else {
-            P.a_lo = P.a_hi = -1;
-            n_items = exh_items_of(U, -1, P.bw, P.xch);
-            prefix = {0, n_items};
+            if (sc->cap_prefix < prefix.size()) {
+                if (sc->d_prefix) cudaFree(sc->d_prefix);
+                sc->cap_prefix = prefix.size() * 2;
+                if ((err = cudaMalloc(&sc->d_prefix, sc->cap_prefix * sizeof(u64))) != cudaSuccess) return (int)err;
+            }
+            if ((err = cudaMemcpyAsync(sc->d_prefix, prefix.data(), prefix.size() * sizeof(u64), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)err;
+            sc->k_U = U; sc->k_bw = P.bw; sc->k_xch = P.xch; sc->k_alo = P.a_lo; sc->k_ahi = P.a_hi;
         }
-        if (n_items >= 6 * slots) break;
+        P.item_prefix = sc->d_prefix;
+        P.n_items = A.n3;
     }
-    if (n_items == 0) { *done = true; return 0; }
-    if (n_items >= 0xffffff00ull) return 0;   // work queue is 32 bit: let the generic kernel take it (never in practice)
-    if (sc->cap_prefix < prefix.size()) {
-        if (sc->d_prefix) cudaFree(sc->d_prefix);
-        sc->cap_prefix = prefix.size() * 2;
-        if ((err = cudaMalloc(&sc->d_prefix, sc->cap_prefix * sizeof(u64))) != cudaSuccess) return (int)err;
+    if (have2) {
+        ExhParams& P = A.p2;
+        for (const auto& cd : cand) {
+            P.bw = cd[0]; P.xch = cd[1];
+            A.n2 = exh_items_of(U, -1, P.bw, P.xch);
+            if (A.n2 + A.n3 >= 6 * slots || (have3 && A.n2 >= slots / 4)) break;
+        }
+        P.n_items = A.n2;
     }
-    if ((err = cudaMemcpyAsync(sc->d_prefix, prefix.data(), prefix.size() * sizeof(u64), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)err;
+    A.n_total = A.n3 + A.n2 + (u64)A.n1_tiles + (u64)A.do_null;
+    if (A.n_total == 0) return 0;
     if ((err = cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
-    P.item_prefix = sc->d_prefix;
-    P.n_items = n_items;
-    P.counter = sc->d_counter;
-    const int blocks = (int)std::min<u64>((n_items + EXH_WARPS - 1) / EXH_WARPS, (u64)sm_count * occ);
-    if (j == 3) exhaustive_reg_kernel<3><<<blocks, EXH_WARPS * 32, 0, stream>>>(L, P, Lg);
-    else exhaustive_reg_kernel<2><<<blocks, EXH_WARPS * 32, 0, stream>>>(L, P, Lg);
+    A.counter = sc->d_counter;
+    const int blocks = (int)std::min<u64>((A.n_total + EXH_WARPS - 1) / EXH_WARPS, (u64)sm_count * occ);
+    exhaustive_all_kernel<<<blocks, EXH_WARPS * 32, 0, stream>>>(L, A, Lg);
     (*launches)++;
-    if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
-    *done = true;
-    return 0;
+    return (int)cudaGetLastError();
 }
 
 }  // namespace pipsort

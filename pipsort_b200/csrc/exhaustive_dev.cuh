@@ -28,6 +28,21 @@ namespace pipsort {
 
 typedef unsigned long long u64;
 
+#ifndef EXH_MINBLOCKS
+#define EXH_MINBLOCKS 3
+#endif
+#ifndef EXH_PREFETCH
+#define EXH_PREFETCH 1
+#endif
+#ifndef EXH_CELLMAJOR
+#define EXH_CELLMAJOR 0
+#endif
+#ifndef EXH_RSCATTER
+#define EXH_RSCATTER 0
+#endif
+#ifndef EXH_DEFER
+#define EXH_DEFER 1
+#endif
 constexpr int EXH_WARPS = 4;          // warps per block
 constexpr int EXH_BW = 32;            // max b-window
 constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
@@ -211,22 +226,15 @@ struct WarpWin {
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
 
+// One work item of size class J (2 or 3): (a, b window, chunk of x tiles).  Warp-collective.
 template <int J>
-__global__ void __launch_bounds__(EXH_WARPS * 32, 3)
-exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) {
+__device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, const unsigned item, WarpWin& win,
+                                         const LocusDev* __restrict__ Lg, const int lane) {
     constexpr bool HAS_A = (J == 3);
-    __shared__ WarpWin wins[EXH_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpWin& win = wins[wib];
     const AccDev& acc = L.acc;
     const int U = L.U;
     const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
-
-    for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(P.counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if ((u64)item >= P.n_items) break;
+    {
 
         // ---- decode the item: a, first b of the window, first x tile, number of x tiles ---------------
         int a = -1, b0, nb, xt0, nxt;
@@ -350,10 +358,34 @@ exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) 
             const int nstates_x = hx[0] && hx[1] ? 3 : (hx[0] || hx[1] ? 1 : 0);
             double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             const bool diag = P.partial || (b0 + nb - 1 >= xt * 32);     // some lane may be inactive at some step
+            double wnext[2];                                             // W[b][x] of the NEXT step (software prefetch)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int lb = win.st[s].locb[0];
+                wnext[s] = (lb >= 0 && hx[s]) ? L.st[s].W[(size_t)lb * L.st[s].ldw + lx[s]] : 0.0;
+            }
 
+            // b cells of the PREVIOUS step: their warp reduction is issued at the top of the next step so that its
+            // shuffle latency overlaps the exp / rsqrt chains (software pipelining)
+            double pend[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            int pend_t = -1;
+            auto reduce_pending = [&]() {
+                double mine = 0.0;
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    double r = pend[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                    if (lane == k) mine = r;
+                }
+                if (lane < 5) win.acc[pend_t][lane] += mine;
+            };
             for (int t = 0; t < nb; t++) {
                 const int b = b0 + t;
                 if (b >= xt * 32 + 31) break;                       // no x of this tile is beyond b
+#if EXH_DEFER
+                if (pend_t >= 0) reduce_pending();
+#endif
                 bool active = xin;
                 if (diag) {
                     active = active && x > b;
@@ -369,8 +401,16 @@ exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) 
                     const int lb = w.locb[t];
                     hb[s] = lb >= 0;
                     double e6 = 0.0, e7 = 0.0;
+#if EXH_PREFETCH
+                    const double Wbx = wnext[s];
+                    if (t + 1 < nb) {
+                        const int lbn = w.locb[t + 1];
+                        wnext[s] = (lbn >= 0 && hx[s]) ? S.W[(size_t)lbn * S.ldw + lx[s]] : 0.0;
+                    }
+#else
+                    const double Wbx = (hb[s] && hx[s]) ? S.W[(size_t)lb * S.ldw + lx[s]] : 0.0;
+#endif
                     if (hb[s] && hx[s]) {
-                        const double Wbx = S.W[(size_t)lb * S.ldw + lx[s]];
                         const double s6 = fma(-Wbx * Wbx, w.invAb[t], Ax[s]);
                         const double r6 = fma(-Wbx, w.ub[t], zx[s]);
                         e6 = extend_fast(w.v2[t], S.hd, r6, s6, bad);
@@ -393,8 +433,51 @@ exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) 
                     for (int s = 0; s < 2; s++) { v[s][4] = 0.0; v[s][5] = 0.0; v[s][6] = 0.0; v[s][7] = 0.0; }
                 }
 
-                // ---- cells: G[snp][state][a'] = sum over the expansions with that SNP in that state ----------
-                // snp 0 = a, 1 = b, 2 = x ; a' = number of OTHER SNPs causal in both studies
+                // ---- cells: g[state][a'] = sum over the expansions with one SNP in that state, a' = number of
+                // OTHER SNPs causal in both studies.  One SNP at a time (9 live sums instead of 27).
+                auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
+                    return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
+                };
+                auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
+                auto cell = [&](const int I, double (&g)[3][3]) {   // I: 0 = a, 1 = b, 2 = x
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+#pragma unroll
+                        for (int r = 0; r < 3; r++) g[q][r] = 0.0;
+#pragma unroll
+                    for (int tx = 0; tx < 3; tx++)
+#pragma unroll
+                        for (int tb = 0; tb < 3; tb++)
+#pragma unroll
+                            for (int ta = 0; ta < (HAS_A ? 3 : 1); ta++) {
+                                const int m0 = (HAS_A && in0(ta) ? 1 : 0) | (in0(tb) ? 2 : 0) | (in0(tx) ? 4 : 0);
+                                const int m1 = (HAS_A && in1(ta) ? 1 : 0) | (in1(tb) ? 2 : 0) | (in1(tx) ? 4 : 0);
+                                const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
+                                const int ti = I == 0 ? ta : (I == 1 ? tb : tx);
+                                g[ti][ac - (ti == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], g[ti][ac - (ti == 2 ? 1 : 0)]);
+                            }
+                };
+#if EXH_CELLMAJOR
+                {   // x cells -> lane registers (flushed after the window)
+                    double g[3][3];
+                    cell(2, g);
+                    const double x1 = wsumX(g[0], false), x2 = wsumX(g[1], false), x3 = wsumX(g[2], true);
+                    accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
+                    accX[YS] += sumY(g[2]);
+                    accX[YN] += sumY(g[0]) + sumY(g[1]);
+                    accT += (x1 + x2) + x3;                                        // every expansion exactly once
+                }
+                if (HAS_A) {   // a cells -> lane registers (flushed at the end of the item)
+                    double g[3][3];
+                    cell(0, g);
+                    accA[X1] += wsumX(g[0], false); accA[X2] += wsumX(g[1], false); accA[X3] += wsumX(g[2], true);
+                    accA[YS] += sumY(g[2]);
+                    accA[YN] += sumY(g[0]) + sumY(g[1]);
+                }
+                // no causal SNP in study 1 (0): every chosen SNP causal in study 0 (1) only  (postcal.cpp:988-1000)
+                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
+                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+#else
                 double G[3][3][3];
 #pragma unroll
                 for (int i = 0; i < 3; i++)
@@ -415,41 +498,83 @@ exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) 
                             G[1][tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[1][tb][ac - (tb == 2 ? 1 : 0)]);
                             if (HAS_A) G[0][ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[0][ta][ac - (ta == 2 ? 1 : 0)]);
                         }
-                auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
-                    return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
-                };
-                auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
                 {
                     const double x1 = wsumX(G[2][0], false), x2 = wsumX(G[2][1], false), x3 = wsumX(G[2][2], true);
                     accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
                     accX[YS] += sumY(G[2][2]);
                     accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
-                    accT += (x1 + x2) + x3;                                        // every expansion exactly once
+                    accT += (x1 + x2) + x3;
                 }
                 if (HAS_A) {
                     accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
                     accA[YS] += sumY(G[0][2]);
                     accA[YN] += sumY(G[0][0]) + sumY(G[0][1]);
                 }
-                // no causal SNP in study 1 (0): every chosen SNP causal in study 0 (1) only  (postcal.cpp:988-1000)
                 accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
                 accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
-                {   // b cells -> shuffle reduction -> shared-memory window accumulators
-                    double vb[5];
-                    vb[X1] = wsumX(G[1][0], false); vb[X2] = wsumX(G[1][1], false); vb[X3] = wsumX(G[1][2], true);
-                    vb[YS] = sumY(G[1][2]);
-                    vb[YN] = sumY(G[1][0]) + sumY(G[1][1]);
-                    double mine = 0.0;
+#endif
+                {   // b cells -> reduce-scatter over the warp (8 shuffles) -> shared-memory window accumulators
+#if EXH_CELLMAJOR
+                    double g[3][3];
+                    cell(1, g);
+#else
+                    double (&g)[3][3] = G[1];
+#endif
+                    double q0 = wsumX(g[0], false), q1 = wsumX(g[1], false), q2 = wsumX(g[2], true);   // X1 X2 X3
+                    double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
+#if EXH_DEFER
+                    pend[0] = q0; pend[1] = q1; pend[2] = q2; pend[3] = q3; pend[4] = q4;
+                    pend_t = t;
+#elif !EXH_RSCATTER
+                    {
+                        double vb[5] = {q0, q1, q2, q3, q4};
+                        double mine = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 5; k++) {
-                        double r = vb[k];
+                        for (int k = 0; k < 5; k++) {
+                            double r = vb[k];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                        if (lane == k) mine = r;
+                            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                            if (lane == k) mine = r;
+                        }
+                        if (lane < 5) win.acc[t][lane] += mine;
                     }
-                    if (lane < 5) win.acc[t][lane] += mine;
+#else
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+                    // round 1 (xor 16): lower half keeps {q0,q1,q2}, upper half keeps {q3,q4}
+                    {
+                        const double s0 = h16 ? q0 : q3, s1 = h16 ? q1 : q4, s2 = h16 ? q2 : 0.0;
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16),
+                                     r2 = __shfl_xor_sync(0xffffffffu, s2, 16);
+                        q0 = (h16 ? q3 : q0) + r0; q1 = (h16 ? q4 : q1) + r1; q2 = (h16 ? 0.0 : q2) + r2;
+                    }
+                    // now lower half: (q0,q1,q2) = partial (X1,X2,X3); upper half: (q0,q1) = partial (YS,YN), q2 = 0
+                    // round 2 (xor 8): sub-half 0 keeps {q0,q1}, sub-half 1 keeps {q2}  (upper half: {q0} / {q1})
+                    {
+                        const double k0 = h16 ? q0 : q0, k1 = h16 ? 0.0 : q1;          // what sub-half 0 keeps
+                        const double o0 = h16 ? q1 : q2;                                // what sub-half 1 keeps
+                        const double s0 = h8 ? k0 : o0, s1 = h8 ? k1 : 0.0;
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+                        q0 = (h8 ? o0 : k0) + r0; q1 = (h8 ? 0.0 : k1) + r1;
+                    }
+                    // lanes 0-7: (q0,q1) = (X1,X2); 8-15: q0 = X3; 16-23: q0 = YS; 24-31: q0 = YN
+                    // round 3 (xor 4): lanes 0-3 keep q0 (X1), lanes 4-7 keep q1 (X2); the others just reduce q0
+                    {
+                        const bool split = lane < 8;
+                        const double s0 = split ? (h4 ? q0 : q1) : q0;
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 4);
+                        q0 = (split ? (h4 ? q1 : q0) : q0) + r0;
+                    }
+                    q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+                    q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+                    // holders: lane 0 X1, lane 4 X2, lane 8 X3, lane 16 YS, lane 24 YN
+                    const int slot = lane == 0 ? X1 : (lane == 4 ? X2 : (lane == 8 ? X3 : (lane == 16 ? YS : (lane == 24 ? YN : -1))));
+                    if (slot >= 0) win.acc[t][slot] += q0;
+#endif
                 }
             }  // b window
+#if EXH_DEFER
+            if (pend_t >= 0) reduce_pending();
+#endif
 
             if (xin) {   // flush the x cells of this tile
 #pragma unroll
@@ -488,6 +613,79 @@ exhaustive_reg_kernel(LocusDev L, ExhParams P, const LocusDev* __restrict__ Lg) 
             if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
         }
         __syncwarp();
+    }
+}
+
+// Size class 1: one lane per union SNP of a 32-wide tile; three expansions at most.  Mantissa/exponent
+// arithmetic straight into the bins (U subsets in total: cost is irrelevant).
+__device__ inline void singles_tile(const LocusDev& L, int tile, int x_lo, int x_hi, int lane) {
+    const AccDev& acc = L.acc;
+    const int x = tile * 32 + lane;
+    unsigned cnt = 0;
+    if (x >= x_lo && x < x_hi) {
+        const int l0 = L.loc[0][x], l1 = L.loc[1][x];
+        const double p0 = L.pi[1][0], p1 = L.pi[1][1];
+        E2 e0{1.0, 0}, e1{1.0, 0};
+        if (l0 >= 0) e0 = E2{L.st[0].e1m[l0], L.st[0].e1n[l0]};
+        if (l1 >= 0) e1 = E2{L.st[1].e1m[l1], L.st[1].e1n[l1]};
+        if (l0 >= 0) {   // causal in study 0 only
+            bin_add(acc, X1, x, p0 * e0.m, e0.n); bin_add(acc, YN, x, e0.m, e0.n);
+            bin_add(acc, SCAL, S_TOTAL, p0 * e0.m, e0.n); bin_add(acc, SCAL, S_NC1, p0 * e0.m, e0.n);
+            cnt++;
+        }
+        if (l1 >= 0) {   // causal in study 1 only
+            bin_add(acc, X2, x, p0 * e1.m, e1.n); bin_add(acc, YN, x, e1.m, e1.n);
+            bin_add(acc, SCAL, S_TOTAL, p0 * e1.m, e1.n); bin_add(acc, SCAL, S_NC0, p0 * e1.m, e1.n);
+            cnt++;
+        }
+        if (l0 >= 0 && l1 >= 0) {   // causal in both
+            const double m = e0.m * e1.m;
+            const int n = e0.n + e1.n;
+            bin_add(acc, X3, x, p1 * m, n); bin_add(acc, YS, x, m, n);
+            bin_add(acc, SCAL, S_TOTAL, p1 * m, n);
+            cnt++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(acc.counters, (u64)cnt);
+}
+
+// All size classes 0..3 of one pipsort_run_exhaustive call in ONE launch: a single work queue whose items
+// are ordered from expensive (triples) to cheap (pairs, tiles of singles, the null configuration).
+struct ExhAll {
+    ExhParams p3, p2;
+    u64 n3, n2;            // number of items of the two register classes
+    int n1_tiles, tile1_0; // size class 1: tiles [tile1_0, tile1_0 + n1_tiles), SNPs [x1_lo, x1_hi)
+    int x1_lo, x1_hi;
+    int do_null;           // rank 0 (the empty configuration) is in range
+    u64 n_total;
+    unsigned* counter;
+};
+
+__global__ void __launch_bounds__(EXH_WARPS * 32, EXH_MINBLOCKS)
+exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
+    __shared__ WarpWin wins[EXH_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpWin& win = wins[wib];
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(A.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((u64)item >= A.n_total) break;
+        if ((u64)item < A.n3) {
+            exh_item<3>(L, A.p3, item, win, Lg, lane);
+        } else if ((u64)item < A.n3 + A.n2) {
+            exh_item<2>(L, A.p2, (unsigned)(item - A.n3), win, Lg, lane);
+        } else if ((u64)item < A.n3 + A.n2 + (u64)A.n1_tiles) {
+            singles_tile(L, A.tile1_0 + (int)(item - A.n3 - A.n2), A.x1_lo, A.x1_hi, lane);
+        } else if (lane == 0) {   // postcal.cpp:793-822: -K/2 - 1 + U log(1-gamma)
+            const double einv = 0.36787944117144233;
+            bin_add(L.acc, SCAL, S_TOTAL, einv, 0);
+            bin_add(L.acc, SCAL, S_NC0, einv, 0);
+            bin_add(L.acc, SCAL, S_NC1, einv, 0);
+            atomicAdd(L.acc.counters, 1ull);
+        }
     }
 }
 

@@ -43,7 +43,21 @@ __device__ __forceinline__ void xadd(XAcc& a, double m, int n) {
 __device__ __forceinline__ void xmerge(XAcc& a, const XAcc& b) { xadd(a, b.M, b.N); }
 
 // exp(t) = m * 2^n with m in [0.70, 1.42];  |t| < 2^30 ln 2.  Cody-Waite reduction + degree-13
-// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18 relative).
+// Taylor polynomial on |r| <= ln2/2 (truncation 4e-18 relative).  Coefficients live in constant memory so
+// that the DFMAs take them as c[bank][offset] operands (no per-use UMOV pairs).
+__constant__ double XEXP_C[12] = {
+    1.6059043836821613e-10,   // 1/13!
+    2.08767569878681e-09,     // 1/12!
+    2.505210838544172e-08,    // 1/11!
+    2.755731922398589e-07,    // 1/10!
+    2.7557319223985893e-06,   // 1/9!
+    2.48015873015873e-05,     // 1/8!
+    1.984126984126984e-04,    // 1/7!
+    1.3888888888888889e-03,   // 1/6!
+    8.333333333333333e-03,    // 1/5!
+    4.1666666666666664e-02,   // 1/4!
+    1.6666666666666666e-01,   // 1/3!
+    0.5};
 __device__ __forceinline__ void xexp(double t, double& m, int& n) {
     const double LOG2E = 1.4426950408889634;
     const double LN2_HI = 6.93147180369123816490e-01;  // low 21 bits zero: k*LN2_HI exact for |k| < 2^21..
@@ -54,20 +68,31 @@ __device__ __forceinline__ void xexp(double t, double& m, int& n) {
     double kf = tmp - MAGIC;
     double r = fma(-kf, LN2_HI, t);
     r = fma(-kf, LN2_LO, r);
-    double p = 1.6059043836821613e-10;         // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);       // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);      // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);      // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);     // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);       // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);      // 1/7!
-    p = fma(p, r, 1.3888888888888889e-03);     // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);      // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);     // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);     // 1/3!
-    p = fma(p, r, 0.5);
+#ifdef XEXP_HORNER
+    double p = XEXP_C[0];
+#pragma unroll
+    for (int i = 1; i < 12; i++) p = fma(p, r, XEXP_C[i]);
     p = fma(p, r, 1.0);
     m = fma(p, r, 1.0);
+#else
+    // Estrin evaluation of sum_{i<=13} r^i / i!  (dependency depth 5 instead of 14)
+    const double r2 = r * r;
+    const double a0 = 1.0 + r;                         // c0 + c1 r
+    const double a1 = fma(XEXP_C[10], r, XEXP_C[11]);  // 1/2! + r/3!
+    const double a2 = fma(XEXP_C[8], r, XEXP_C[9]);    // 1/4! + r/5!
+    const double a3 = fma(XEXP_C[6], r, XEXP_C[7]);    // 1/6! + r/7!
+    const double a4 = fma(XEXP_C[4], r, XEXP_C[5]);    // 1/8! + r/9!
+    const double a5 = fma(XEXP_C[2], r, XEXP_C[3]);    // 1/10! + r/11!
+    const double a6 = fma(XEXP_C[0], r, XEXP_C[1]);    // 1/12! + r/13!
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double r8 = r4 * r4;
+    const double d0 = fma(b1, r4, b0);
+    const double d1 = fma(a6, r4, b2);
+    m = fma(d1, r8, d0);
+#endif
 }
 
 // natural log of an accumulator; caller handles M == 0 (empty)
