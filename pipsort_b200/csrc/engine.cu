@@ -188,10 +188,24 @@ struct pipsort_engine {
 
 namespace {
 
+// Stream-ordered allocation from the device's default memory pool: after the first engine on a device the
+// pool serves create/destroy without touching the driver allocator (the locus arrays of a fine-mapping run
+// are created and destroyed once per locus).
+int pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device < 64 && done[device]) return 0;
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    if (device < 64) done[device] = true;
+    return 0;
+}
+
 template <class T>
 int dev_alloc(pipsort_engine* e, T** p, size_t count) {
     void* q = nullptr;
-    CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    CU(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), e->own_stream));
     e->allocs.push_back(q);
     *p = static_cast<T*>(q);
     return 0;
@@ -244,7 +258,12 @@ void pipsort_destroy(pipsort_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (void* p : e->allocs) cudaFree(p);
+    if (e->own_stream) {
+        if (e->exh.d_prefix) cudaFreeAsync(e->exh.d_prefix, e->own_stream);
+        if (e->exh.d_counter) cudaFreeAsync(e->exh.d_counter, e->own_stream);
+        for (void* p : e->allocs) cudaFreeAsync(p, e->own_stream);
+        cudaStreamSynchronize(e->own_stream);
+    }
     if (e->d_idx) cudaFree(e->d_idx);
     if (e->d_upd) cudaFree(e->d_upd);
     if (e->d_out) cudaFree(e->d_out);
@@ -253,8 +272,7 @@ void pipsort_destroy(pipsort_engine* e) {
     if (e->evk0) cudaEventDestroy(e->evk0);
     if (e->evk1) cudaEventDestroy(e->evk1);
     if (e->l2_scratch) cudaFree(e->l2_scratch);
-    if (e->exh.d_prefix) cudaFree(e->exh.d_prefix);
-    if (e->exh.d_counter) cudaFree(e->exh.d_counter);
+
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -267,9 +285,11 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     if (device < 0 || device >= ndev) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev);
     CU(cudaSetDevice(device));
     e->device = device;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    e->sm_count = prop.multiProcessorCount;
+    CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        int rcp = pool_setup(device);
+        if (rcp) return rcp;
+    }
     CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     CU(cudaEventCreate(&e->ev0));
@@ -315,11 +335,21 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     LocusDev& L = e->L;
     memset(&L, 0, sizeof L);
     L.U = U;
-    int* d_tmp = nullptr;
     int rc;
-    if ((rc = dev_upload(e, &d_tmp, u2i.data(), U))) return rc;
-    L.u2i = d_tmp;
-    if ((rc = dev_upload(e, &e->d_snp_map, lc->snp_map, (size_t)2 * U))) return rc;
+    // one packed upload of all the small integer arrays: u2i[U] | snp_map[2U] | loc0[U] | loc1[U] | orig0 | orig1
+    int* d_ints = nullptr;
+    size_t orig_off[2];
+    {
+        std::vector<int> pack;
+        pack.reserve((size_t)5 * U + e->orig[0].size() + e->orig[1].size());
+        pack.insert(pack.end(), u2i.begin(), u2i.end());
+        pack.insert(pack.end(), lc->snp_map, lc->snp_map + (size_t)2 * U);
+        for (int s = 0; s < S; s++) pack.insert(pack.end(), e->loc[s].begin(), e->loc[s].end());
+        for (int s = 0; s < S; s++) { orig_off[s] = pack.size(); pack.insert(pack.end(), e->orig[s].begin(), e->orig[s].end()); }
+        if ((rc = dev_upload(e, &d_ints, pack.data(), pack.size()))) return rc;
+    }
+    L.u2i = d_ints;
+    e->d_snp_map = d_ints + U;
     size_t soff = 0, zoff = 0;
     double maxexp_nats = 0.0, minexp_bits = 0.0;
     for (int s = 0; s < S; s++) {
@@ -330,11 +360,11 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         double *d_sigma = nullptr, *d_zraw = nullptr, *W = nullptr, *A = nullptr, *z = nullptr, *invA = nullptr, *u = nullptr,
                *e1m = nullptr;
         int *d_orig = nullptr, *d_loc = nullptr, *e1n = nullptr;
-        CU(cudaMalloc(&d_sigma, std::max<size_t>((size_t)n_raw * n_raw, 1) * sizeof(double)));
+        CU(cudaMallocAsync(&d_sigma, std::max<size_t>((size_t)n_raw * n_raw, 1) * sizeof(double), e->stream));
         CU(cudaMemcpyAsync(d_sigma, lc->sigma + soff, (size_t)n_raw * n_raw * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         if ((rc = dev_upload(e, &d_zraw, lc->z + zoff, n_raw))) return rc;
-        if ((rc = dev_upload(e, &d_orig, e->orig[s].data(), n))) return rc;
-        if ((rc = dev_upload(e, &d_loc, e->loc[s].data(), U))) return rc;
+        d_orig = d_ints + orig_off[s];
+        d_loc = d_ints + (size_t)3 * U + (size_t)s * U;
         if ((rc = dev_alloc(e, &W, (size_t)n * ldw))) return rc;
         if ((rc = dev_alloc(e, &A, n)) || (rc = dev_alloc(e, &z, n)) || (rc = dev_alloc(e, &invA, n)) ||
             (rc = dev_alloc(e, &u, n)) || (rc = dev_alloc(e, &e1m, n)) || (rc = dev_alloc(e, &e1n, n)))
@@ -346,8 +376,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             e->launches += 2;
         }
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(e->stream));
-        CU(cudaFree(d_sigma));
+        CU(cudaFreeAsync(d_sigma, e->stream));
         StudyDev& st = L.st[s];
         st.W = W; st.A = A; st.z = z; st.invA = invA; st.u = u; st.e1m = e1m; st.e1n = e1n;
         st.n = n; st.ldw = ldw; st.hd = 0.5 * d;
@@ -394,24 +423,35 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     L.null_l = (-lc->K / 2 - std::sqrt(std::fabs(1.0))) + U * std::log(1.0 - gam);   // postcal.cpp:802-803
 
     // ---- expansion tables: digit i of e = state of SNP i (0: study 0 only, 1: study 1 only, 2: both) ---
-    for (int k = 0; k <= KMAX; k++) {
-        int n3 = 1;
-        for (int i = 0; i < k; i++) n3 *= 3;
-        std::vector<uint32_t> tab(n3);
-        for (int x = 0; x < n3; x++) {
-            uint32_t m0 = 0, m1 = 0, a = 0;
-            int v = x;
-            for (int i = 0; i < k; i++, v /= 3) {
-                const int t = v % 3;
-                if (t != 1) m0 |= 1u << i;
-                if (t != 0) m1 |= 1u << i;
-                if (t == 2) a++;
-            }
-            tab[x] = m0 | m1 << 8 | a << 16;
+    // locus independent: built once per device and shared by every engine of the process
+    {
+        static uint32_t* cache[64][KMAX + 1] = {{nullptr}};
+        const int dslot = device & 63;
+        if (!cache[dslot][0]) {
+            size_t total = 0;
+            int n3s[KMAX + 1];
+            for (int k = 0, n3 = 1; k <= KMAX; k++, n3 *= 3) { n3s[k] = n3; total += n3; }
+            std::vector<uint32_t> tab(total);
+            size_t o = 0;
+            for (int k = 0; k <= KMAX; k++)
+                for (int x = 0; x < n3s[k]; x++) {
+                    uint32_t m0 = 0, m1 = 0, a = 0;
+                    int v = x;
+                    for (int i = 0; i < k; i++, v /= 3) {
+                        const int t = v % 3;
+                        if (t != 1) m0 |= 1u << i;
+                        if (t != 0) m1 |= 1u << i;
+                        if (t == 2) a++;
+                    }
+                    tab[o++] = m0 | m1 << 8 | a << 16;
+                }
+            uint32_t* d_tab = nullptr;
+            CU(cudaMalloc(&d_tab, total * sizeof(uint32_t)));      // lives as long as the process
+            CU(cudaMemcpy(d_tab, tab.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            o = 0;
+            for (int k = 0; k <= KMAX; k++) { cache[dslot][k] = d_tab + o; o += n3s[k]; }
         }
-        uint32_t* d_tab = nullptr;
-        if ((rc = dev_upload(e, &d_tab, tab.data(), n3))) return rc;
-        L.exptab[k] = d_tab;
+        for (int k = 0; k <= KMAX; k++) L.exptab[k] = cache[dslot][k];
     }
 
     // ---- accumulator store ------------------------------------------------------------------------------

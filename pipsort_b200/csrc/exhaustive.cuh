@@ -82,7 +82,7 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     const int U = L.U;
     cudaError_t err;
     if (!sc->d_counter) {
-        if ((err = cudaMalloc(&sc->d_counter, sizeof(unsigned))) != cudaSuccess) return (int)err;
+        if ((err = cudaMallocAsync(&sc->d_counter, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
         if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
     }
     ExhAll A;
@@ -120,9 +120,9 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
             prefix.push_back(0);
             for (int a = P.a_lo; a <= P.a_hi; a++) prefix.push_back(prefix.back() + exh_items_of(U, a, P.bw, P.xch));
             if (sc->cap_prefix < prefix.size()) {
-                if (sc->d_prefix) cudaFree(sc->d_prefix);
+                if (sc->d_prefix) cudaFreeAsync(sc->d_prefix, stream);
                 sc->cap_prefix = prefix.size() * 2;
-                if ((err = cudaMalloc(&sc->d_prefix, sc->cap_prefix * sizeof(u64))) != cudaSuccess) return (int)err;
+                if ((err = cudaMallocAsync(&sc->d_prefix, sc->cap_prefix * sizeof(u64), stream)) != cudaSuccess) return (int)err;
             }
             if ((err = cudaMemcpyAsync(sc->d_prefix, prefix.data(), prefix.size() * sizeof(u64), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)err;
             sc->k_U = U; sc->k_bw = P.bw; sc->k_xch = P.xch; sc->k_alo = P.a_lo; sc->k_ahi = P.a_hi;
