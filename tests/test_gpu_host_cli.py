@@ -1,0 +1,70 @@
+"""The C++ host (pipsort_b200/host -> pipsort_b200/lib/PIPSORT): same command line, same six output files.
+
+Every golden case stores the files the UNMODIFIED reference wrote (tests/golden/make_golden.py); the host CLI in
+front of the GPU engine must reproduce them byte for byte (6 significant digits), including the stochastic
+shotgun search (seed 12345, identical sampling sequence) and the appended _log.txt."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import GOLDEN, ROOT, golden, has_golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["small_c1_p075", "small_c2_p025", "small_c2_p075", "small_c3_p075", "small_c3_p0", "small_c3_g005_t1_s3",
+         "small_sss_c3_p075", "small_sss_c2_p025", "example_c1_p025", "example_c2_p025", "example_sss_c2_p025"]
+MAPS = {"small_example": "eur_afr_small_test_snp_map", "example": "snp_map"}
+
+
+def host_bin():
+    from pipsort_b200 import build
+    build.build_engine()
+    p = build.build_host()
+    assert p and os.path.exists(p)
+    return p
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cli_reproduces_reference_files(name):
+    if not has_golden(name):
+        pytest.skip("golden not generated")
+    g = golden(name)
+    d = os.path.join(GOLDEN, g["dataset"])
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "o")
+        cmd = [host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", MAPS[g["dataset"]], "-n", g["sample_sizes"],
+               "-o", out] + g["args"]
+        p = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        for flag in g["stdout_flags"]:
+            assert flag in p.stdout
+        for suf, want in g["files"].items():
+            with open(f"{out}_{suf}.txt") as f:
+                got = f.read()
+            assert got == want, f"{name}: {suf} differs"
+
+
+def test_cli_shipped_example_files():
+    """run_example.sh of the reference: -c 2 -n 334324,6771 -p 0.25 against the six expected_* files it ships."""
+    d = os.path.join(GOLDEN, "example")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "results")
+        p = subprocess.run([host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", "snp_map", "-n", "334324,6771", "-o", out,
+                            "-c", "2", "-p", "0.25"], cwd=d, capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        for suf in ["study0_post", "study1_post", "study0_set", "study1_set", "nocausal", "shared_pips"]:
+            with open(f"{out}_{suf}.txt") as f, open(os.path.join(d, f"expected_{suf}.txt")) as w:
+                assert f.read() == w.read(), suf
+
+
+def test_cli_flag_quirks():
+    """-m falls through into -n (pipsort.cpp:128-132): with -n BEFORE -m the sample sizes are overwritten by the map
+    path and the run dies with the reference's format error; missing required flags exit 1."""
+    d = os.path.join(GOLDEN, "small_example")
+    p = subprocess.run([host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-n", "7000,7000", "-m",
+                        "eur_afr_small_test_snp_map", "-o", "/tmp/x"], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 1 and "sample size is not in the right format" in p.stdout
+    p = subprocess.run([host_bin(), "-l", "ldfiles.txt"], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 1 and "are required" in p.stdout
