@@ -239,6 +239,21 @@ def score_union_configs(L: Locus, idx: np.ndarray, make_updates=None, state: Res
     return out, Result(tot.value, post, nc, sp, sl, nl)
 
 
+def given_configs(L: Locus, configs: np.ndarray):
+    """postcal.cpp:400-714 (-b/-d/-e): configs = int16[num_configs][num_groups] of global SNP indices, negative = none.
+    Returns (rc, Result): rc 0 ok, 2 = the reference's "This did not work as expected" exit, 3 = out-of-range entry."""
+    n, sig, z, d, smap = L.flat()
+    cfg = np.ascontiguousarray(configs, dtype=np.int16)
+    nn, ng = cfg.shape
+    post = np.zeros(L.N); nc = np.zeros(L.S); sp = np.zeros(L.U); sl = np.zeros(L.U); nl = np.zeros(L.U)
+    tot = C.c_double(); ne = _u64()
+    rc = lib().oracle_given_configs(L.S, _i(n), _d(sig), _d(z), C.c_double(L.K), _d(d), L.U, _i(smap),
+                                    C.c_double(L.gamma), C.c_double(L.p), cfg.ctypes.data_as(C.POINTER(C.c_int16)),
+                                    C.c_int64(nn), int(ng), C.byref(tot), _d(post), _d(nc), _d(sp), _d(sl), _d(nl),
+                                    C.byref(ne))
+    return rc, Result(tot.value, post, nc, sp, sl, nl, int(ne.value))
+
+
 def sss(L: Locus, c: int, max_iter: int = 1000, trace_cap: int = 1000) -> Result:
     n, sig, z, d, smap = L.flat()
     post = np.zeros(L.N); nc = np.zeros(L.S); sp = np.zeros(L.U); sl = np.zeros(L.U); nl = np.zeros(L.U)

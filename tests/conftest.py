@@ -43,11 +43,19 @@ def dataset_paths(name):
 
 def args_to_params(args):
     """['-c','2','-p','0.25', ...] -> dict with the reference's defaults (pipsort.cpp:69-77)."""
-    prm = dict(c=3, p=0.75, gamma=0.01, t=0.52, s=5.2, q=0)
-    key = {"-c": "c", "-p": "p", "-g": "gamma", "-t": "t", "-s": "s", "-q": "q"}
+    prm = dict(c=3, p=0.75, gamma=0.01, t=0.52, s=5.2, q=0, b=None, d=0, e=0)
+    key = {"-c": "c", "-p": "p", "-g": "gamma", "-t": "t", "-s": "s", "-q": "q", "-b": "b", "-d": "d", "-e": "e"}
     for k, v in zip(args[::2], args[1::2]):
-        prm[key[k]] = int(v) if k in ("-c", "-q") else float(v)
+        prm[key[k]] = v if k == "-b" else (int(v) if k in ("-c", "-q", "-d", "-e") else float(v))
     return prm
+
+
+def given_config_matrix(prm):
+    """The int16 matrix a golden case was run on ('@rel/path' is relative to tests/golden)."""
+    import numpy as np
+    path = prm["b"]
+    path = os.path.join(GOLDEN, path[1:]) if path.startswith("@") else path
+    return np.fromfile(path, dtype=np.int16).reshape(prm["d"], prm["e"]), path
 
 
 _locus_cache = {}

@@ -46,7 +46,29 @@ CASES = {
     "example_c1_p025": (EX, ["-c", "1", "-p", "0.25"], True),
     "example_c2_p025": (EX, ["-c", "2", "-p", "0.25"], True),           # run_example.sh:1
     "example_sss_c2_p025": (EX, ["-c", "2", "-p", "0.25", "-q", "1"], False),
+    # explicit configurations (-b/-d/-e, postcal.cpp:400-714); the OpenMP loop there updates noCausal / sharedPips /
+    # sharedLL / notSharedLL without synchronisation too (:481-483, :650, :664-669) -> one thread
+    "small_given_72x5": (SMALL, ["-b", "@test_optional_configs/all_configs_int16", "-d", "72", "-e", "5"], True),   # tests/test_optional_configs/run_test.sh:1
+    "small_given_mixed_p025": (SMALL, ["-b", "@test_optional_configs/small_mixed_int16", "-d", "96", "-e", "6", "-p", "0.25"], True),
+    "example_given_mixed": (EX, ["-b", "@test_optional_configs/example_mixed_int16", "-d", "240", "-e", "7", "-p", "0.25"], True),
 }
+
+
+def make_config_matrix(path, n_snps, rows, groups, seed):
+    """A seeded int16 matrix in the layout utils/construct_configs_all_studies.py:104-158 writes: every row lists
+    global SNP indices (offset_s + i) in increasing order with -1 for unused groups; includes all-(-1) rows, rows
+    with several causal SNPs per study and rows that hit the same union SNP in both studies."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    N = int(sum(n_snps))
+    M = np.full((rows, groups), -1, dtype=np.int16)
+    for r in range(rows):
+        k = int(rng.integers(0, groups + 1)) if r % 11 else 0
+        pick = np.sort(rng.choice(N, size=k, replace=False))
+        cols = np.sort(rng.choice(groups, size=k, replace=False))
+        M[r, cols] = pick
+    M.tofile(path)
+    return M
 
 
 def run_case(name):
@@ -57,7 +79,8 @@ def run_case(name):
         env["OMP_THREAD_LIMIT"] = "1"
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "o")
-        cmd = [DUMP, "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", ds["map"], "-n", ds["n"], "-o", out] + extra
+        xargs = [os.path.join(HERE, a[1:]) if a.startswith("@") else a for a in extra]
+        cmd = [DUMP, "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", ds["map"], "-n", ds["n"], "-o", out] + xargs
         t = time.time()
         p = subprocess.run(cmd, cwd=d, env=env, capture_output=True, text=True)
         dt = time.time() - t
@@ -79,5 +102,10 @@ def run_case(name):
 
 if __name__ == "__main__":
     assert os.path.exists(DUMP), "build oracle/_ref first: make -C oracle ref"
+    oc = os.path.join(HERE, "test_optional_configs")
+    if not os.path.exists(os.path.join(oc, "small_mixed_int16")):
+        make_config_matrix(os.path.join(oc, "small_mixed_int16"), [5, 6], 96, 6, 1)
+    if not os.path.exists(os.path.join(oc, "example_mixed_int16")):
+        make_config_matrix(os.path.join(oc, "example_mixed_int16"), [222, 219], 240, 7, 2)
     for nm in (sys.argv[1:] or CASES.keys()):
         run_case(nm)

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, args_to_params, golden, has_golden, oracle_locus
+from conftest import GOLDEN, args_to_params, given_config_matrix, golden, has_golden, oracle_locus
 from oracle import oracle as O
 
 # log-likelihoods within 1e-10 relative, PIPs within 1e-8 absolute (BASELINE.json north_star)
@@ -46,6 +46,30 @@ def test_exhaustive_matches_reference_dump(name):
     assert L.K == pytest.approx(g["K"], rel=1e-12)
     r = O.exhaustive(L, prm["c"])
     check_against_golden(r, g)
+
+
+GIVEN = ["small_given_72x5", "small_given_mixed_p025", "example_given_mixed"]
+
+
+@pytest.mark.parametrize("name", GIVEN)
+def test_given_configs_match_reference_dump(name):
+    """-b/-d/-e (postcal.cpp:400-714) against 17-digit dumps of the reference on the same int16 matrices."""
+    g = golden(name)
+    prm = args_to_params(g["args"])
+    L = oracle_locus(g["dataset"], p=prm["p"], gamma=prm["gamma"], s=prm["s"], t=prm["t"])
+    cfg, _ = given_config_matrix(prm)
+    rc, r = O.given_configs(L, cfg)
+    assert rc == 0 and r.n_eval == prm["d"]
+    check_against_golden(r, g)
+
+
+def test_given_configs_rejects_what_the_reference_rejects():
+    L = oracle_locus("small_example")
+    ok = np.array([[0, 5, -1]], dtype=np.int16)
+    assert O.given_configs(L, ok)[0] == 0
+    assert O.given_configs(L, np.array([[5, 0, -1]], dtype=np.int16))[0] == 2      # out of order: "did not work"
+    assert O.given_configs(L, np.array([[3, 3, -1]], dtype=np.int16))[0] == 2      # duplicate entry
+    assert O.given_configs(L, np.array([[0, 11, -1]], dtype=np.int16))[0] == 3     # >= N
 
 
 def test_counts():
