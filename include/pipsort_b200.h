@@ -26,6 +26,7 @@ extern "C" {
 #define PIPSORT_E_STUDIES 3  /* number of studies != 2 (postcal.cpp:20-23 exits for > 2)           */
 #define PIPSORT_E_RANGE 4    /* rank space / exponent range overflow                               */
 #define PIPSORT_E_SINGULAR 5 /* a causal sub-block lost positive definiteness (postcal.cpp:291-294) */
+#define PIPSORT_E_CONFIG 6   /* an explicit configuration row the reference aborts on (postcal.cpp:593-596) */
 
 #define PIPSORT_KMAX 8       /* max union SNPs per configuration on the scoring path               */
 #define PIPSORT_JMAX_EXH 3   /* exhaustive path: union subsets of size <= 3 (postcal.cpp:760-762)  */
@@ -108,6 +109,18 @@ int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n
 /* Same with device-resident idx / make_updates / out buffers (no host copies, asynchronous). */
 int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
                                        const uint8_t* d_make_updates, double* d_out_max_abs_l);
+
+/* Replaces PostCal::computeTotalLikelihoodGivenConfigs (postcal.cpp:400-714; flags -b/-d/-e, pipsort.cpp:153-161):
+ * configs is the int16 matrix [num_configs][num_groups] the reference mmaps (postcal.cpp:429-447), every row ONE
+ * configuration given as global SNP indices offset_s + i (postcal.cpp:868-872) in increasing order, negative =
+ * unused group; rows without any entry are the null configuration (postcal.cpp:461-492).  Accumulates into the
+ * engine's accumulators (read them with pipsort_read_accumulators; pipsort_config_count gives the reference's
+ * mycount).  A row the reference aborts on ("This did not work as expected", postcal.cpp:593-596: entries out of
+ * order or repeated), an entry >= N, or more than PIPSORT_KMAX causal SNPs in one study fails with
+ * PIPSORT_E_CONFIG (reported by this call for host buffers, by the next pipsort_read_accumulators for the
+ * asynchronous device-buffer variant).                                                             */
+int pipsort_score_given_configs(pipsort_engine* e, const int16_t* configs, int64_t num_configs, int num_groups);
+int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_configs, int64_t num_configs, int num_groups);
 
 /* Reads the accumulators into PostCal's result arrays (any member of `out` may be NULL).  Replaces the
  * reads of totalLikeLihoodLOG / postValues / noCausal / sharedPips / sharedLL / notSharedLL by

@@ -63,13 +63,16 @@ struct AccDev {
     int Upad;
     unsigned long long* counters;  // [0] expanded configurations evaluated, [1] error flags
 };
-enum ErrFlag : unsigned long long { ERR_RANGE = 1ull, ERR_NOT_PD = 2ull };
+enum ErrFlag : unsigned long long { ERR_RANGE = 1ull, ERR_NOT_PD = 2ull, ERR_BAD_CONFIG = 4ull };
 
 struct LocusDev {
     StudyDev st[NSTUDY];
     int U;
     const int* loc[NSTUDY];   // [U] internal union index -> study-local index or -1
     const int* u2i;           // [U] snp_map (user) union index -> internal union index
+    const int* raw2loc[NSTUDY];  // [n_raw] study index as in the LD / z files -> study-local internal index or -1
+    const int* loc2u[NSTUDY];    // [n] study-local internal index -> internal union index
+    int n_raw[NSTUDY];           // PostCal::num_snps_all
     double pi[KMAX + 1][KMAX + 1];        // pi'(j,a)
     double logprior[KMAX + 1][KMAX + 1];  // log_prior(j,a), complete (postcal.cpp:19-59)
     double neg_half_K;                    // -K/2

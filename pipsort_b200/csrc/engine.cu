@@ -14,6 +14,7 @@
 #include "../../include/pipsort_b200.h"
 #include "common.cuh"
 #include "exhaustive.cuh"
+#include "given.cuh"
 #include "score.cuh"
 
 using namespace pipsort;
@@ -336,19 +337,33 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     memset(&L, 0, sizeof L);
     L.U = U;
     int rc;
-    // one packed upload of all the small integer arrays: u2i[U] | snp_map[2U] | loc0[U] | loc1[U] | orig0 | orig1
+    // one packed upload of all the small integer arrays:
+    //   u2i[U] | snp_map[2U] | loc0[U] | loc1[U] | orig0 | orig1 | raw2loc0 | raw2loc1 | loc2u0 | loc2u1
     int* d_ints = nullptr;
-    size_t orig_off[2];
+    size_t orig_off[2], r2l_off[2], l2u_off[2];
     {
         std::vector<int> pack;
-        pack.reserve((size_t)5 * U + e->orig[0].size() + e->orig[1].size());
+        pack.reserve((size_t)5 * U + 2 * (e->orig[0].size() + e->orig[1].size()) + lc->num_snps[0] + lc->num_snps[1]);
         pack.insert(pack.end(), u2i.begin(), u2i.end());
         pack.insert(pack.end(), lc->snp_map, lc->snp_map + (size_t)2 * U);
         for (int s = 0; s < S; s++) pack.insert(pack.end(), e->loc[s].begin(), e->loc[s].end());
         for (int s = 0; s < S; s++) { orig_off[s] = pack.size(); pack.insert(pack.end(), e->orig[s].begin(), e->orig[s].end()); }
+        for (int s = 0; s < S; s++) {
+            r2l_off[s] = pack.size();
+            std::vector<int> r2l(lc->num_snps[s], -1);
+            for (size_t l = 0; l < e->orig[s].size(); l++) r2l[e->orig[s][l]] = (int)l;
+            pack.insert(pack.end(), r2l.begin(), r2l.end());
+        }
+        for (int s = 0; s < S; s++) {
+            l2u_off[s] = pack.size();
+            std::vector<int> l2u(e->orig[s].size(), -1);
+            for (int i = 0; i < U; i++) if (e->loc[s][i] >= 0) l2u[e->loc[s][i]] = i;
+            pack.insert(pack.end(), l2u.begin(), l2u.end());
+        }
         if ((rc = dev_upload(e, &d_ints, pack.data(), pack.size()))) return rc;
     }
     L.u2i = d_ints;
+    for (int s = 0; s < S; s++) { L.raw2loc[s] = d_ints + r2l_off[s]; L.loc2u[s] = d_ints + l2u_off[s]; L.n_raw[s] = lc->num_snps[s]; }
     e->d_snp_map = d_ints + U;
     size_t soff = 0, zoff = 0;
     double maxexp_nats = 0.0, minexp_bits = 0.0;
@@ -599,12 +614,66 @@ int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n
     return 0;
 }
 
+int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_configs, int64_t num_configs, int num_groups) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (num_configs < 0 || num_groups < 0) return fail(PIPSORT_E_ARG, "negative matrix dimension");
+    if (num_configs == 0) return 0;
+    if (!d_configs && num_groups > 0) return fail(PIPSORT_E_ARG, "null configs");
+    CU(cudaSetDevice(e->device));
+    const int64_t blocks = (num_configs + GIVEN_THREADS - 1) / GIVEN_THREADS;
+    if (blocks > 0x7fffffff) return fail(PIPSORT_E_ARG, "too many configurations for one call");
+    given_configs_kernel<<<(unsigned)blocks, GIVEN_THREADS, 0, e->stream>>>(e->L, d_configs, num_configs, num_groups);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int check_flags(pipsort_engine* e);
+
+int pipsort_score_given_configs(pipsort_engine* e, const int16_t* configs, int64_t num_configs, int num_groups) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (num_configs < 0 || num_groups < 0) return fail(PIPSORT_E_ARG, "negative matrix dimension");
+    if (num_configs == 0) return 0;
+    if (!configs && num_groups > 0) return fail(PIPSORT_E_ARG, "null configs");
+    CU(cudaSetDevice(e->device));
+    // stream the matrix through two pinned-size device chunks so that arbitrarily large files (it is mmapped by the
+    // caller, postcal.cpp:429) never need more than a bounded staging buffer
+    const int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)64 << 20) / std::max(1, num_groups * 2));
+    int16_t* d_buf[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    const int64_t cap = std::min(rows_per_chunk, num_configs);
+    int rc = 0;
+    for (int i = 0; i < 2 && !rc; i++) {
+        if (cudaMallocAsync((void**)&d_buf[i], (size_t)cap * std::max(1, num_groups) * sizeof(int16_t), e->stream) != cudaSuccess ||
+            cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(PIPSORT_E_CUDA, "staging buffer allocation failed");
+        if (num_configs <= cap) break;
+    }
+    int cur = 0;
+    for (int64_t r0 = 0; r0 < num_configs && !rc; r0 += cap, cur ^= 1) {
+        const int64_t nr = std::min(cap, num_configs - r0);
+        if (r0 >= 2 * cap && cudaEventSynchronize(done[cur]) != cudaSuccess) { rc = fail(PIPSORT_E_CUDA, "event sync failed"); break; }
+        if (num_groups > 0 &&
+            cudaMemcpyAsync(d_buf[cur], configs + r0 * num_groups, (size_t)nr * num_groups * sizeof(int16_t), cudaMemcpyHostToDevice,
+                            e->stream) != cudaSuccess) { rc = fail(PIPSORT_E_CUDA, "H2D copy of the configuration matrix failed"); break; }
+        rc = pipsort_score_given_configs_device(e, d_buf[cur], nr, num_groups);
+        if (!rc && cudaEventRecord(done[cur], e->stream) != cudaSuccess) rc = fail(PIPSORT_E_CUDA, "event record failed");
+    }
+    for (int i = 0; i < 2; i++) {
+        if (d_buf[i]) cudaFreeAsync(d_buf[i], e->stream);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    if (rc) return rc;
+    return check_flags(e);
+}
+
 static int check_flags(pipsort_engine* e) {
     u64 c[2];
     CU(cudaMemcpyAsync(c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (c[1] & ERR_NOT_PD) return fail(PIPSORT_E_SINGULAR, "matrix is singular");   // postcal.cpp:291-294
     if (c[1] & ERR_RANGE) return fail(PIPSORT_E_RANGE, "a contribution fell outside the provisioned exponent range");
+    if (c[1] & ERR_BAD_CONFIG) return fail(PIPSORT_E_CONFIG, "This did not work as expected");          // postcal.cpp:593-596
     return 0;
 }
 

@@ -58,6 +58,8 @@ def lib():
         L.pipsort_score_union_configs.argtypes = [vp, C.POINTER(C.c_int32), C.c_int64, i32, C.POINTER(C.c_uint8),
                                                   C.POINTER(C.c_double)]
         L.pipsort_score_union_configs_device.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
+        L.pipsort_score_given_configs.argtypes = [vp, C.POINTER(C.c_int16), C.c_int64, i32]
+        L.pipsort_score_given_configs_device.argtypes = [vp, vp, C.c_int64, i32]
         L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
         L.pipsort_finalize.argtypes = [vp]
         L.pipsort_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -204,6 +206,20 @@ class Engine:
     def score_union_configs_device(self, d_idx_ptr, n, kmax, d_upd_ptr, d_out_ptr):
         _check(lib().pipsort_score_union_configs_device(self._h, C.c_void_p(d_idx_ptr), int(n), int(kmax),
                                                         C.c_void_p(d_upd_ptr), C.c_void_p(d_out_ptr)))
+
+    def score_given_configs(self, configs):
+        """computeTotalLikelihoodGivenConfigs (postcal.cpp:400-714, -b/-d/-e): int16[num_configs][num_groups] of global
+        SNP indices, negative = unused group; accumulates (call reset() first for a fresh PostCal)."""
+        cfg = np.ascontiguousarray(configs, dtype=np.int16)
+        if cfg.ndim != 2:
+            raise ValueError("configs must be a num_configs x num_groups matrix")
+        _check(lib().pipsort_score_given_configs(self._h, cfg.ctypes.data_as(C.POINTER(C.c_int16)), cfg.shape[0],
+                                                 cfg.shape[1]))
+
+    def compute_total_likelihood_given_configs(self, configs):
+        self.reset()
+        self.score_given_configs(configs)
+        return self.read()
 
     def read(self) -> Results:
         total = np.zeros(1)

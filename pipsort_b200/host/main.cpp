@@ -1,7 +1,7 @@
 // PIPSORT command line (pipsort.cpp:68-228) in front of the GPU engine.  Flag string, defaults and quirks are
 // the reference's: `-m` falls through into `-n` (so -n must come after -m), flags without an argument exit 1,
-// -r / -a / -k / -f only influence stdout.  Not supported (exit 1 with a message): -b/-d/-e (explicit
-// configurations), more or fewer than two studies.
+// -r / -a / -k / -f only influence stdout; -b/-d/-e select the explicit-configuration path (postcal.cpp:400-714).
+// Not supported (exit 1 with a message): more or fewer than two studies.
 #include <unistd.h>
 
 #include <cstdio>
@@ -53,10 +53,12 @@ int pipsort_main(int argc, char* argv[]) {
         std::cout << "Error: -l, -z, -o, and -n are required" << std::endl;
         std::exit(1);
     }
-    if (!configsFile.empty()) {
-        (void)num_configs; (void)num_groups;
-        std::cout << "Error: explicit configurations (-b/-d/-e) are not supported by the GPU engine yet" << std::endl;
-        std::exit(1);
+    if (!configsFile.empty()) {                  // pipsort.cpp:189-197 (no exit after the num_groups message: sic)
+        if (num_configs <= 0) {
+            std::cout << "Number of configs must be greater than 0" << std::endl;
+            std::exit(1);
+        }
+        if (num_groups <= 0) std::cout << "Number of groups must be greater than 0" << std::endl;
     }
     const std::vector<std::string> ldDir = read_dir(ldFile), zDir = read_dir(zFile);
     const std::vector<int> sample_sizes = read_sigma(sample_s);
@@ -64,7 +66,7 @@ int pipsort_main(int argc, char* argv[]) {
         std::cout << "Error: LD files, Z files, and sample sizes do not match in number" << std::endl;
         std::exit(1);
     }
-    Model m(ldDir, zDir, snpMapFile, sss_flag == 1, sample_sizes, outputFileName, totalCausalSNP, sharing_param, rho, gamma,
+    Model m(ldDir, zDir, snpMapFile, configsFile, num_configs, num_groups, sss_flag == 1, sample_sizes, outputFileName, totalCausalSNP, sharing_param, rho, gamma,
             tau_sqr, sigma_g_squared, cutoff_threshold, device);
     m.run();
     m.finishUp();

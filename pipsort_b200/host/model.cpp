@@ -12,7 +12,7 @@
 namespace pipsort_host {
 
 Model::Model(const std::vector<std::string>& ldDir, const std::vector<std::string>& zDir, const std::string& snpMapFile,
-             bool do_sss, const std::vector<int>& sample_sizes, const std::string& outName, int totalCausalSNP,
+             const std::string& configsFile, int num_configs, int num_groups, bool do_sss, const std::vector<int>& sample_sizes, const std::string& outName, int totalCausalSNP,
              double sharing_param, double rho_, double gamma, double tau_sqr, double sigma_g_squared, double cutoff, int device)
     : num_of_studies((int)ldDir.size()), rho(rho_), cutoff_threshold(cutoff), outputFileName(outName) {
     std::vector<std::vector<double>> sigma, z_score;
@@ -60,7 +60,7 @@ Model::Model(const std::vector<std::string>& ldDir, const std::vector<std::strin
         K += p.K;
     }
     post = new PostCal(sigma, z_score, K, do_sss, totalCausalSNP, &snpNames, sharing_param, gamma, tau_sqr, sigma_g_squared,
-                       sample_sizes, num_snps_all, idx_to_snp_map, all_snp_pos, device);
+                       sample_sizes, num_snps_all, idx_to_snp_map, all_snp_pos, device, configsFile, num_configs, num_groups);
 }
 
 Model::~Model() { delete post; }

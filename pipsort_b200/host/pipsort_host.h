@@ -43,13 +43,15 @@ public:
             bool do_sss, int MAX_causal, const std::vector<std::vector<std::string>>* SNP_NAME, double sharing_param,
             double gamma, double t_squared, double s_squared, const std::vector<int>& sample_sizes,
             const std::vector<int>& num_snps_all, const std::vector<std::vector<int>>& idx_to_snp_map,
-            const std::vector<std::string>& all_snp_pos, int device = 0);
+            const std::vector<std::string>& all_snp_pos, int device = 0, const std::string& configsFile = "",
+            int num_configs = 0, int num_groups = 0);
     ~PostCal();
     PostCal(const PostCal&) = delete;
     PostCal& operator=(const PostCal&) = delete;
 
     double computeTotalLikelihood();          // postcal.cpp:716
     double sss_computeTotalLikelihood();      // sss_postcal.cpp:102
+    double computeTotalLikelihoodGivenConfigs();   // postcal.cpp:400
     std::vector<char> findOptimalSetGreedy(std::vector<int>* rank, double inputRho, const std::string& outputFileName,
                                            double cutoff_threshold);          // postcal.cpp:1128
     void printPost2File(const std::string& fileName);                         // postcal.h:288
@@ -69,6 +71,8 @@ private:
     const std::vector<std::vector<std::string>>* SNP_NAME;
     std::vector<std::string> all_snp_pos;
     std::map<std::vector<int>, double> config_hashmap;     // postcal.h:98
+    std::string configsFile;                               // postcal.h:84-86 (-b / -d / -e)
+    int num_configs = 0, num_groups = 0;
 };
 
 // neighbourhoods of the stochastic shotgun search (sss_postcal.cpp:20-99)
@@ -80,7 +84,7 @@ std::vector<std::vector<int>> get_nbdzero(const std::vector<int>& causal_locs, i
 class Model {
 public:
     Model(const std::vector<std::string>& ldDir, const std::vector<std::string>& zDir, const std::string& snpMapFile,
-          bool do_sss, const std::vector<int>& sample_sizes, const std::string& outputFileName, int totalCausalSNP,
+          const std::string& configsFile, int num_configs, int num_groups, bool do_sss, const std::vector<int>& sample_sizes, const std::string& outputFileName, int totalCausalSNP,
           double sharing_param, double rho, double gamma, double tau_sqr, double sigma_g_squared, double cutoff_threshold,
           int device = 0);
     ~Model();

@@ -10,6 +10,11 @@
 #include <numeric>
 #include <random>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "pipsort_host.h"
 
 namespace pipsort_host {
@@ -46,9 +51,10 @@ PostCal::PostCal(const std::vector<std::vector<double>>& sigma_eff, const std::v
                  bool do_sss_, int MAX_causal, const std::vector<std::vector<std::string>>* names, double sharing_param,
                  double gamma, double t_squared, double s_squared, const std::vector<int>& sample_sizes,
                  const std::vector<int>& num_snps, const std::vector<std::vector<int>>& idx_to_snp_map,
-                 const std::vector<std::string>& snp_pos, int device)
+                 const std::vector<std::string>& snp_pos, int device, const std::string& configsFile_, int num_configs_,
+                 int num_groups_)
     : num_of_studies((int)num_snps.size()), maxCausalSNP(MAX_causal), do_sss(do_sss_), num_snps_all(num_snps),
-      SNP_NAME(names), all_snp_pos(snp_pos) {
+      SNP_NAME(names), all_snp_pos(snp_pos), configsFile(configsFile_), num_configs(num_configs_), num_groups(num_groups_) {
     totalSnpCount = std::accumulate(num_snps_all.begin(), num_snps_all.end(), 0);
     unionSnpCount = (int)all_snp_pos.size();
     postValues.assign(totalSnpCount, 0.0);
@@ -109,6 +115,38 @@ double PostCal::computeTotalLikelihood() {
     uint64_t total = 0;
     check(pipsort_total_ranks(eng, maxCausalSNP, &total));
     check(pipsort_run_exhaustive(eng, maxCausalSNP, 0, total));
+    read_results();
+    printf("num total configs = %llu\n", (unsigned long long)n_configs);
+    return totalLikeLihoodLOG;
+}
+
+// postcal.cpp:400-714: the rows of the mmapped int16 matrix are the configurations (flags -b / -d / -e)
+double PostCal::computeTotalLikelihoodGivenConfigs() {
+    printf("Input configs given\n");
+    printf("num total configs = %d\n", 0);
+    std::cout << "Max Causal = " << maxCausalSNP << std::endl;
+    std::cout << "Union Snp Count = " << unionSnpCount << std::endl;
+    // util.cpp:26-49 safe_mmap_read_only + the size check of postcal.cpp:429-437
+    const int fd = open(configsFile.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0) {
+        printf("Could not open %s\n", configsFile.c_str());
+        printf("mmap did not succeed\n");
+        std::exit(1);
+    }
+    if (fstat(fd, &st) < 0) {
+        printf("mmap did not succeed\n");
+        std::exit(1);
+    }
+    const size_t len = (size_t)st.st_size;
+    void* map = len ? mmap(nullptr, len, PROT_READ, MAP_SHARED, fd, 0) : nullptr;
+    close(fd);
+    if ((size_t)num_configs * (size_t)num_groups * sizeof(int16_t) != len || (len && map == MAP_FAILED)) {
+        printf("config file is not the expected size\n");
+        std::exit(1);
+    }
+    check(pipsort_score_given_configs(eng, static_cast<const int16_t*>(map), num_configs, num_groups));
+    if (len) munmap(map, len);
     read_results();
     printf("num total configs = %llu\n", (unsigned long long)n_configs);
     return totalLikeLihoodLOG;
@@ -258,7 +296,8 @@ std::vector<char> PostCal::findOptimalSetGreedy(std::vector<int>* rank, double i
                                                 double cutoff_threshold) {
     std::vector<char> causalSet(totalSnpCount, '0');
     const auto start = std::chrono::steady_clock::now();
-    if (do_sss) totalLikeLihoodLOG = sss_computeTotalLikelihood();
+    if (!configsFile.empty()) totalLikeLihoodLOG = computeTotalLikelihoodGivenConfigs();     // postcal.cpp:1134-1140
+    else if (do_sss) totalLikeLihoodLOG = sss_computeTotalLikelihood();
     else totalLikeLihoodLOG = computeTotalLikelihood();
     const auto end = std::chrono::steady_clock::now();
     std::cout << "Time to eval all= " << std::chrono::duration_cast<std::chrono::microseconds>(end - start).count() << "[µs]"

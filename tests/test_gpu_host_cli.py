@@ -14,7 +14,8 @@ from conftest import GOLDEN, ROOT, golden, has_golden
 pytestmark = pytest.mark.gpu
 
 CASES = ["small_c1_p075", "small_c2_p025", "small_c2_p075", "small_c3_p075", "small_c3_p0", "small_c3_g005_t1_s3",
-         "small_sss_c3_p075", "small_sss_c2_p025", "example_c1_p025", "example_c2_p025", "example_sss_c2_p025"]
+         "small_sss_c3_p075", "small_sss_c2_p025", "example_c1_p025", "example_c2_p025", "example_sss_c2_p025",
+         "small_given_72x5", "small_given_mixed_p025", "example_given_mixed"]
 MAPS = {"small_example": "eur_afr_small_test_snp_map", "example": "snp_map"}
 
 
@@ -35,7 +36,7 @@ def test_cli_reproduces_reference_files(name):
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "o")
         cmd = [host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", MAPS[g["dataset"]], "-n", g["sample_sizes"],
-               "-o", out] + g["args"]
+               "-o", out] + [os.path.join(GOLDEN, a[1:]) if a.startswith("@") else a for a in g["args"]]
         p = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         for flag in g["stdout_flags"]:
@@ -68,3 +69,10 @@ def test_cli_flag_quirks():
     assert p.returncode == 1 and "sample size is not in the right format" in p.stdout
     p = subprocess.run([host_bin(), "-l", "ldfiles.txt"], cwd=d, capture_output=True, text=True)
     assert p.returncode == 1 and "are required" in p.stdout
+    # -b with the wrong -d: "config file is not the expected size" (postcal.cpp:434-437); -d 0: pipsort.cpp:190-193
+    base = [host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", "eur_afr_small_test_snp_map", "-n", "7000,7000", "-o", "/tmp/x",
+            "-b", os.path.join(GOLDEN, "test_optional_configs", "all_configs_int16")]
+    p = subprocess.run(base + ["-d", "71", "-e", "5"], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 1 and "config file is not the expected size" in p.stdout
+    p = subprocess.run(base + ["-d", "0", "-e", "5"], cwd=d, capture_output=True, text=True)
+    assert p.returncode == 1 and "Number of configs must be greater than 0" in p.stdout
