@@ -42,6 +42,9 @@ WORKLOADS = {
     "A300c2": (300, 0.8, 2),
     "B1500c3": (1500, 0.8, 3),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of one exhaustive_all_kernel launch, from the `ncu --set full` captures
+# summarised in profiles/r1_v3_exhaustive_all_*.txt (the loci are L2 resident: LD is read from HBM once)
+TRAFFIC_BYTES = {"B150c3": 579840 + 3584, "B1500c3": 19257856 + 290048}
 METRIC = "causal configurations/sec (exhaustive, c=3, synthetic 150-SNP/study two-ancestry locus)"
 UNIT = "configs/s"
 
@@ -242,6 +245,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pipsort_b200 as P
+    from pipsort_b200 import distributed as D
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,6 +254,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keeps NCCL's version banner off stdout: ONE JSON line is the contract
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     # everything (engine kernels, NCCL all-reduce, timing events) is enqueued on ONE non-default stream
@@ -270,14 +276,9 @@ def main():
         stream = torch.cuda.current_stream()
         e.set_stream(stream.cuda_stream)
         b = e.shard_ranks(c, world)
-        lo, hi = b[rank], b[rank + 1]
-        acc = e.accumulator_tensor()
 
         def step():
-            e.reset()
-            e.run_exhaustive(c, lo, hi)
-            if world > 1:
-                dist.all_reduce(acc)          # ONE NCCL collective on the accumulator store
+            D.run_exhaustive_sharded(e, c, bounds=b)   # reset + this rank's launch + ONE NCCL all-reduce(sum) of the store
             e.finalize()
 
         for _ in range(warmup):
@@ -306,14 +307,13 @@ def main():
         kms = [k for k in kms if k is not None]
         tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
         k_ms = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
-        cnt = torch.tensor([e.config_count()], dtype=torch.int64, device=dev)   # last step's count on this rank
+        cnt = e.config_count()            # the count rides in the all-reduced store: the whole job's on every rank
         if world > 1:
             dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(cnt)
         res = e.read() if rank == 0 else None
         e.close()
-        assert int(cnt.item()) == total_configs, (int(cnt.item()), total_configs)
+        assert cnt == total_configs, (cnt, total_configs)
         return dict(total_configs=total_configs, ms_per_step=float(tot_ms.item()) / steps, kernel_ms=float(k_ms.item()),
                     launches=launches, wall_ms_per_step=1e3 * t_wall / steps, clocks=clk, result=res)
 
@@ -328,13 +328,9 @@ def main():
         def once():
             e = P.Engine(L.num_snps, sig.numpy(), z.numpy(), L.d, L.K, L.snp_map, gamma=L.gamma,
                          sharing_param=L.sharing_param, max_causal=c, device=local)
-            b = e.shard_ranks(c, world)
-            e.run_exhaustive(c, b[rank], b[rank + 1])
             if world > 1:
-                e.sync()
-                dist.all_reduce(e.accumulator_tensor())
-                torch.cuda.synchronize()
-            r = e.read()
+                D.bind_engine_to_current_stream(e)
+            r = D.compute_total_likelihood_sharded(e, c)
             e.close()
             return r
 
@@ -360,7 +356,7 @@ def main():
     # the dominant launch on rank r covers 1/world of the class (work-weighted shard)
     achieved = cf / world / (main_m["kernel_ms"] * 1e-3) / 1e12
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
-            "traffic": None,
+            "traffic": TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
             "note": ("FP64 vector pipe (DFMA), no tensor cores / not HBM bound; achieved = ALGORITHMIC flops of the size-c class "
                      f"({cf:.4g} flop, {cf / max(cn, 1):.1f}/configuration, SURVEY.md 8d) per launch / its CUDA-event duration "
                      f"({main_m['kernel_ms']:.4f} ms); peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "

@@ -38,6 +38,9 @@ extern "C" {
 #define PIPSORT_GENERIC_ONLY 2u /* testing: run every subset-size class through the generic (warp per configuration)
                                   kernel instead of the register kernel                                */
 
+#define PIPSORT_RAW_LD 4u     /* pipsort_locus.sigma holds the LD matrices as read from the -l files and K is ignored: the engine
+                                 runs Model's pre-processing (PSD shift + eigen-decomposition, model.h:171-264) on the device */
+
 typedef struct pipsort_engine pipsort_engine;
 
 /* Locus description = the PostCal constructor arguments the likelihood actually consumes
@@ -75,6 +78,24 @@ typedef struct pipsort_outputs {
     double* sharedLL;     /* [U]                                                                    */
     double* notSharedLL;  /* [U]   (postcal.cpp:1014-1016)                                          */
 } pipsort_outputs;
+
+/* Replaces Model's per-study pre-processing (model.h:171-264): makeSigmaPositiveSemiDefinite (util.cpp:195-226: +0.01
+ * on the diagonal until the LU determinant is > 0, an underflowed determinant counting as not positive), eigen_decomp
+ * (util.cpp:228-263), |Omega| (model.h:227), B = |Omega|^(1/2) Q^T and S' = |Omega|^(-1/2) Q^T z (model.h:230-255) --
+ * returned in the form the engine consumes: sigma_eff = B^T B (n x n, host), K = S'^T S', plus the diagonal shift.
+ * Runs on `device` (cuSOLVER LU / symmetric eigensolver + the engine's own kernels); host buffers in and out.
+ * pipsort_create with PIPSORT_RAW_LD does the same without the round trip through host memory; its findings are read
+ * back with pipsort_prep_info_get.                                                                   */
+typedef struct pipsort_prep_info {
+    double add_diag;        /* a_s: what makeSigmaPositiveSemiDefinite added to the diagonal                      */
+    double K;               /* S'_s^T S'_s                                                                        */
+    double min_abs_eig;     /* smallest |eigenvalue| of the shifted matrix                                        */
+    int32_t n_negative;     /* eigenvalues whose sign model.h:227 flips                                           */
+    int32_t psd_iterations; /* LU factorizations the PSD loop needed                                              */
+} pipsort_prep_info;
+int pipsort_preprocess_study(int device, int32_t n, const double* ld, const double* z, double* sigma_eff,
+                             pipsort_prep_info* info);
+int pipsort_prep_info_get(const pipsort_engine* e, int study, pipsort_prep_info* info);
 
 /* Replaces the PostCal constructor (postcal.h:118-195): copies the locus to `device` (CUDA ordinal),
  * builds the device-side tables and zeroes the accumulators.                                       */
@@ -148,7 +169,8 @@ int pipsort_enumerate(pipsort_engine* e, int c, uint64_t rank, uint32_t expansio
 
 /* Multi-GPU: the accumulators are one flat device array of doubles whose element-wise SUM over
  * engines working on disjoint rank ranges of the same locus is the accumulator state of the union
- * (SURVEY.md section 8e).  One process per GPU combines them with a single NCCL all-reduce(sum) on
+ * (SURVEY.md section 8e); the configuration count and the error counters live in its last elements, so
+ * the one sum carries them too.  One process per GPU combines them with a single NCCL all-reduce(sum) on
  * this buffer; a single process driving several devices can use pipsort_merge.                    */
 int pipsort_accumulator_buffer(pipsort_engine* e, void** device_ptr, uint64_t* num_doubles);
 int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copies across devices)  */
@@ -156,6 +178,10 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copi
 /* Split [0,total) into `parts` contiguous rank ranges of roughly equal work (expanded configurations
  * weighted); bounds receives parts+1 values.                                                      */
 int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds);
+/* The same split computed from the snp_map alone (int32[2][U] as in pipsort_locus; flags as given to pipsort_create):
+ * pure host arithmetic, needs no device -- a launcher can plan the shards before any GPU is touched.             */
+int pipsort_shard_ranks_for_map(const int32_t* snp_map, int32_t union_count, int c, int parts, uint32_t flags,
+                                uint64_t* bounds);
 
 /* Stream the engine works on (cudaStream_t as void*), and a blocking sync on it.  pipsort_set_stream
  * makes the engine issue all further work on a caller-owned stream (e.g. the one a NCCL all-reduce of

@@ -61,9 +61,12 @@ struct AccDev {
     int NB;
     int bias;
     int Upad;
-    unsigned long long* counters;  // [0] expanded configurations evaluated, [1] error flags
+    double* counters;  // tail of the same allocation as bins: [0] expanded configurations evaluated (the reference's
+                       // mycount; exact below 2^53), [1 + f] number of times error f was raised.  Doubles, so that the
+                       // ONE all-reduce(sum) that combines the stores of several GPUs carries them as well.
 };
-enum ErrFlag : unsigned long long { ERR_RANGE = 1ull, ERR_NOT_PD = 2ull, ERR_BAD_CONFIG = 4ull };
+enum ErrFlag : int { ERR_RANGE = 0, ERR_NOT_PD = 1, ERR_BAD_CONFIG = 2, NERRFLAG = 3 };
+constexpr int NCOUNTER = 1 + NERRFLAG;
 
 struct LocusDev {
     StudyDev st[NSTUDY];
@@ -81,6 +84,11 @@ struct LocusDev {
     AccDev acc;
 };
 
+__device__ __forceinline__ void count_add(const AccDev& a, unsigned long long n) { atomicAdd(a.counters, (double)n); }
+__device__ __forceinline__ void flag_set(const AccDev& a, ErrFlag f) {
+    if (*(volatile double*)(a.counters + 1 + f) == 0.0) atomicAdd(a.counters + 1 + f, 1.0);   // rare: error path
+}
+
 __device__ __forceinline__ double* bin_ptr(const AccDev& a, int slot, int g) {
     return a.bins + (size_t)slot * a.NB * a.Upad + g;
 }
@@ -94,7 +102,7 @@ __device__ __forceinline__ void bin_add(const AccDev& a, int slot, int g, double
     M = __hiloint2double(hi - (e << 20), __double2loint(M));   // mantissa in [1,2)
     int t = N + e + a.bias;
     int b = t >> 9;
-    if (b < 0 || b >= a.NB) { atomicOr(a.counters + 1, (unsigned long long)ERR_RANGE); return; }
+    if (b < 0 || b >= a.NB) { flag_set(a, ERR_RANGE); return; }
     atomicAdd(bin_ptr(a, slot, g) + (size_t)b * a.Upad, M * pow2c(t & 511));
 }
 

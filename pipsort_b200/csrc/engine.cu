@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "exhaustive.cuh"
 #include "given.cuh"
+#include "prep.cuh"
 #include "score.cuh"
 
 using namespace pipsort;
@@ -185,6 +186,8 @@ struct pipsort_engine {
     int score_smem_set = 0;
     ExhScratch exh;
     bool use_reg_kernel = true;
+    PrepResult prep[2];             // PIPSORT_RAW_LD: what the on-device pre-processing found per study
+    bool prepped = false;
 };
 
 namespace {
@@ -367,6 +370,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->d_snp_map = d_ints + U;
     size_t soff = 0, zoff = 0;
     double maxexp_nats = 0.0, minexp_bits = 0.0;
+    double K_total = (flags & PIPSORT_RAW_LD) ? 0.0 : lc->K;
     for (int s = 0; s < S; s++) {
         const int n_raw = lc->num_snps[s], n = (int)e->orig[s].size();
         const int ldw = (n + 3) & ~3;
@@ -378,6 +382,13 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         CU(cudaMallocAsync(&d_sigma, std::max<size_t>((size_t)n_raw * n_raw, 1) * sizeof(double), e->stream));
         CU(cudaMemcpyAsync(d_sigma, lc->sigma + soff, (size_t)n_raw * n_raw * sizeof(double), cudaMemcpyHostToDevice, e->stream));
         if ((rc = dev_upload(e, &d_zraw, lc->z + zoff, n_raw))) return rc;
+        if (flags & PIPSORT_RAW_LD) {   // model.h:171-264 on the device: PSD shift + eigen-decomposition -> effective LD, K_s
+            std::string why;
+            const int prc = prep_study_device(e->stream, n_raw, d_sigma, d_zraw, &e->prep[s], &why, &e->launches);
+            if (prc) { cudaFreeAsync(d_sigma, e->stream); return fail(prc == -3 ? PIPSORT_E_RANGE : PIPSORT_E_CUDA, "pre-processing of study %d: %s", s, why.c_str()); }
+            K_total += e->prep[s].K;
+            e->prepped = true;
+        }
         d_orig = d_ints + orig_off[s];
         d_loc = d_ints + (size_t)3 * U + (size_t)s * U;
         if ((rc = dev_alloc(e, &W, (size_t)n * ldw))) return rc;
@@ -403,7 +414,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             const int o = e->orig[s][i];
             const double zi = lc->z[zoff + o];
             z2.push_back(zi * zi);
-            maxdiag = std::max(maxdiag, std::fabs(lc->sigma[soff + (size_t)o * n_raw + o]));
+            maxdiag = std::max(maxdiag, std::fabs(lc->sigma[soff + (size_t)o * n_raw + o]) + e->prep[s].add_diag);
         }
         std::sort(z2.begin(), z2.end(), std::greater<double>());
         double top = 0.0;
@@ -434,8 +445,9 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             L.pi[j][a] = std::exp(rel);                       // 0 when p == 1 and a < j
             if (j <= e->kb && std::isfinite(rel)) minpi = std::min(minpi, rel);
         }
-    L.neg_half_K = -0.5 * lc->K;
-    L.null_l = (-lc->K / 2 - std::sqrt(std::fabs(1.0))) + U * std::log(1.0 - gam);   // postcal.cpp:802-803
+    e->K = K_total;
+    L.neg_half_K = -0.5 * K_total;
+    L.null_l = (-K_total / 2 - std::sqrt(std::fabs(1.0))) + U * std::log(1.0 - gam);   // postcal.cpp:802-803
 
     // ---- expansion tables: digit i of e = state of SNP i (0: study 0 only, 1: study 1 only, 2: both) ---
     // locus independent: built once per device and shared by every engine of the process
@@ -478,13 +490,12 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     acc.bias = (((int)std::ceil(-minexp_bits) + 511) / 512 + 1) * 512;
     acc.NB = ((int)std::ceil(maxexp_bits) + acc.bias) / 512 + 2;
     acc.Upad = std::max((U + 3) & ~3, 4);
-    e->bins_len = (size_t)NSLOT * acc.NB * acc.Upad;
+    e->bins_len = (size_t)NSLOT * acc.NB * acc.Upad + NCOUNTER;   // the counters ride in the tail of the store
     if ((rc = dev_alloc(e, &acc.bins, e->bins_len))) return rc;
-    if ((rc = dev_alloc(e, &acc.counters, 2))) return rc;
+    acc.counters = acc.bins + (e->bins_len - NCOUNTER);
     if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U))) return rc;
     e->h_res.resize(3 + (size_t)5 * U);
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
-    CU(cudaMemsetAsync(acc.counters, 0, 2 * sizeof(u64), e->stream));
     if ((rc = dev_upload(e, &e->d_L, &e->L, 1))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     return 0;
@@ -505,11 +516,52 @@ int pipsort_create(const pipsort_locus* lc, int device, uint32_t flags, pipsort_
     return 0;
 }
 
+int pipsort_preprocess_study(int device, int32_t n, const double* ld, const double* z, double* sigma_eff, pipsort_prep_info* info) {
+    if (n < 0 || (n > 0 && (!ld || !z || !sigma_eff))) return fail(PIPSORT_E_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PIPSORT_E_CUDA, "no CUDA device available (the engine has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    int rcp = pool_setup(device);
+    if (rcp) return rcp;
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    double *dA = nullptr, *dz = nullptr;
+    const size_t nn = (size_t)n * n;
+    PrepResult r;
+    std::string why;
+    unsigned long long launches = 0;
+    int prc = 0;
+    cudaError_t err = cudaMallocAsync(&dA, std::max<size_t>(nn, 1) * sizeof(double), st);
+    if (err == cudaSuccess) err = cudaMallocAsync(&dz, std::max<size_t>(n, 1) * sizeof(double), st);
+    if (err == cudaSuccess && n) err = cudaMemcpyAsync(dA, ld, nn * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess && n) err = cudaMemcpyAsync(dz, z, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) prc = prep_study_device(st, n, dA, dz, &r, &why, &launches);
+    if (err == cudaSuccess && !prc && n) err = cudaMemcpyAsync(sigma_eff, dA, nn * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (dA) cudaFreeAsync(dA, st);
+    if (dz) cudaFreeAsync(dz, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    if (err != cudaSuccess) return fail(PIPSORT_E_CUDA, "pre-processing failed: %s", cudaGetErrorString(err));
+    if (prc) return fail(prc == -3 ? PIPSORT_E_RANGE : PIPSORT_E_CUDA, "pre-processing: %s", why.c_str());
+    if (info) { info->add_diag = r.add_diag; info->K = r.K; info->min_abs_eig = r.min_abs_eig; info->n_negative = r.n_negative; info->psd_iterations = r.psd_iterations; }
+    return 0;
+}
+
+int pipsort_prep_info_get(const pipsort_engine* e, int study, pipsort_prep_info* info) {
+    if (!e || !info || study < 0 || study > 1) return fail(PIPSORT_E_ARG, "bad argument");
+    if (!e->prepped) return fail(PIPSORT_E_ARG, "the engine was not created with PIPSORT_RAW_LD");
+    const PrepResult& r = e->prep[study];
+    info->add_diag = r.add_diag; info->K = r.K; info->min_abs_eig = r.min_abs_eig; info->n_negative = r.n_negative; info->psd_iterations = r.psd_iterations;
+    return 0;
+}
+
 int pipsort_reset(pipsort_engine* e) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     CU(cudaMemsetAsync(e->L.acc.bins, 0, e->bins_len * sizeof(double), e->stream));
-    CU(cudaMemsetAsync(e->L.acc.counters, 0, 2 * sizeof(u64), e->stream));
     return 0;
 }
 
@@ -668,12 +720,12 @@ int pipsort_score_given_configs(pipsort_engine* e, const int16_t* configs, int64
 }
 
 static int check_flags(pipsort_engine* e) {
-    u64 c[2];
+    double c[NCOUNTER];
     CU(cudaMemcpyAsync(c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    if (c[1] & ERR_NOT_PD) return fail(PIPSORT_E_SINGULAR, "matrix is singular");   // postcal.cpp:291-294
-    if (c[1] & ERR_RANGE) return fail(PIPSORT_E_RANGE, "a contribution fell outside the provisioned exponent range");
-    if (c[1] & ERR_BAD_CONFIG) return fail(PIPSORT_E_CONFIG, "This did not work as expected");          // postcal.cpp:593-596
+    if (c[1 + ERR_NOT_PD] != 0.0) return fail(PIPSORT_E_SINGULAR, "matrix is singular");   // postcal.cpp:291-294
+    if (c[1 + ERR_RANGE] != 0.0) return fail(PIPSORT_E_RANGE, "a contribution fell outside the provisioned exponent range");
+    if (c[1 + ERR_BAD_CONFIG] != 0.0) return fail(PIPSORT_E_CONFIG, "This did not work as expected");   // postcal.cpp:593-596
     return 0;
 }
 
@@ -731,10 +783,10 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
 int pipsort_config_count(pipsort_engine* e, uint64_t* out) {
     if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
     CU(cudaSetDevice(e->device));
-    u64 c = 0;
+    double c = 0;
     CU(cudaMemcpyAsync(&c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    *out = c;
+    *out = (uint64_t)c;
     return 0;
 }
 
@@ -774,8 +826,6 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
         return fail(PIPSORT_E_ARG, "engines were not created from the same locus");
     CU(cudaSetDevice(src->device));
     CU(cudaStreamSynchronize(src->stream));
-    u64 cs[2], cd[2];
-    CU(cudaMemcpy(cs, src->L.acc.counters, sizeof cs, cudaMemcpyDeviceToHost));
     CU(cudaSetDevice(dst->device));
     double* tmp = nullptr;
     const double* from = src->L.acc.bins;
@@ -789,20 +839,40 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(dst->stream));
     if (tmp) CU(cudaFree(tmp));
-    CU(cudaMemcpy(cd, dst->L.acc.counters, sizeof cd, cudaMemcpyDeviceToHost));
-    cd[0] += cs[0];
-    cd[1] |= cs[1];
-    CU(cudaMemcpy(dst->L.acc.counters, cd, sizeof cd, cudaMemcpyHostToDevice));
-    return 0;
+    return 0;   // the configuration count and the error counters are part of the store
 }
+
+static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds);
 
 int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds) {
     if (!e || !bounds || parts < 1) return fail(PIPSORT_E_ARG, "bad argument");
+    return shard_by_types(e->types, c, parts, bounds);
+}
+
+int pipsort_shard_ranks_for_map(const int32_t* snp_map, int32_t union_count, int c, int parts, uint32_t flags, uint64_t* bounds) {
+    if ((!snp_map && union_count) || union_count < 0 || !bounds || parts < 1) return fail(PIPSORT_E_ARG, "bad argument");
+    const int U = union_count;
+    std::vector<int> types(U);
+    for (int g = 0; g < U; g++) {
+        const int a = snp_map[g], b = snp_map[U + g];
+        types[g] = (a >= 0 && b >= 0) ? 0 : (a >= 0 ? 1 : (b >= 0 ? 2 : 3));
+    }
+    if (!(flags & PIPSORT_KEEP_ORDER)) std::stable_sort(types.begin(), types.end());   // the engine's internal relabelling
+    return shard_by_types(types, c, parts, bounds);
+}
+
+static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds) {
+    if (c < 0) return fail(PIPSORT_E_ARG, "c must be >= 0");
+    const int U = (int)types.size(), cc = std::min(c, U);
     uint64_t total = 0;
-    int rc = pipsort_total_ranks(e, c, &total);
-    if (rc) return rc;
-    const int U = e->U, cc = std::min(c, U);
-    WorkModel wm(e->types, std::max(cc, 1));
+    {
+        bool ovf = false;
+        for (int j = 0; j <= cc; j++) {
+            total += binom_host(U, j, &ovf);
+            if (ovf || total >> 63) return fail(PIPSORT_E_RANGE, "rank space exceeds 2^63 (U=%d, c=%d)", U, c);
+        }
+    }
+    WorkModel wm(types, std::max(cc, 1));
     // segments of consecutive ranks (size class j, smallest element g) with their work estimate
     struct Seg { u64 begin, count; double work; };
     std::vector<Seg> segs;

@@ -1,6 +1,7 @@
 // Exhaustive path: device code in exhaustive_dev.cuh, host-side work decomposition + launch below.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -103,6 +104,11 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     }
     const int occ = std::max(1, sc->occ);
     const u64 slots = (u64)sm_count * occ * EXH_WARPS;
+    static const int per_slot = [] {   // items per resident warp (tuning knob, default 6)
+        const char* v = getenv("PIPSORT_EXH_ITEMS_PER_SLOT");
+        const int k = v ? atoi(v) : 0;
+        return k > 0 ? k : 6;
+    }();
     // granularity: large items amortise the per-item setup, but there must be enough of them to balance
     const int cand[][2] = {{32, 1 << 20}, {32, 16}, {32, 8}, {32, 4}, {32, 2}, {32, 1}, {16, 1}, {8, 1}};
     std::vector<u64> prefix;
@@ -113,7 +119,7 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
             u64 n = 0;
             for (int a = P.a_lo; a <= P.a_hi; a++) n += exh_items_of(U, a, P.bw, P.xch);
             A.n3 = n;
-            if (n >= 6 * slots) break;
+            if (n >= (u64)per_slot * slots) break;
         }
         if (A.n3 >= 0xfff00000ull) return (int)cudaErrorInvalidValue;   // 32-bit work queue (never in practice)
         if (!(sc->k_U == U && sc->k_bw == P.bw && sc->k_xch == P.xch && sc->k_alo == P.a_lo && sc->k_ahi == P.a_hi)) {
@@ -135,7 +141,7 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         for (const auto& cd : cand) {
             P.bw = cd[0]; P.xch = cd[1];
             A.n2 = exh_items_of(U, -1, P.bw, P.xch);
-            if (A.n2 + A.n3 >= 6 * slots || (have3 && A.n2 >= slots / 4)) break;
+            if (A.n2 + A.n3 >= (u64)per_slot * slots || (have3 && A.n2 >= slots / 4)) break;
         }
         P.n_items = A.n2;
     }

@@ -155,7 +155,7 @@ __device__ __noinline__ void slow_subset(const LocusDev& L, int a, int b, int x)
         const double s7 = fma(-tt * tt, i22, cx), r7 = fma(-tt * r2, i22, rx);
         E[s][7] = extend(E[s][3], S.hd, r7, s7, bad);
     }
-    if (bad) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+    if (bad) flag_set(acc, ERR_NOT_PD);
     // numerator exponents carry the penalties of the SNPs the study lacks; reference exponents do not
     auto fam = [&](int s, int m, int ref) -> double {
         int p = 0;
@@ -608,9 +608,9 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 bin_add(acc, SCAL, S_TOTAL, r[5], 0);
                 bin_add(acc, SCAL, S_NC0, r[6], 0);
                 bin_add(acc, SCAL, S_NC1, r[7], 0);
-                atomicAdd(acc.counters, (u64)cnt);
+                count_add(acc, (u64)cnt);
             }
-            if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+            if (__any_sync(0xffffffffu, bad) && lane == 0) flag_set(acc, ERR_NOT_PD);
         }
         __syncwarp();
     }
@@ -648,7 +648,7 @@ __device__ inline void singles_tile(const LocusDev& L, int tile, int x_lo, int x
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0 && cnt) atomicAdd(acc.counters, (u64)cnt);
+    if (lane == 0 && cnt) count_add(acc, (u64)cnt);
 }
 
 // All size classes 0..3 of one pipsort_run_exhaustive call in ONE launch: a single work queue whose items
@@ -684,7 +684,7 @@ exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
             bin_add(L.acc, SCAL, S_TOTAL, einv, 0);
             bin_add(L.acc, SCAL, S_NC0, einv, 0);
             bin_add(L.acc, SCAL, S_NC1, einv, 0);
-            atomicAdd(L.acc.counters, 1ull);
+            count_add(L.acc, 1ull);
         }
     }
 }

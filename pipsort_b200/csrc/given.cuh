@@ -78,7 +78,7 @@ given_configs_kernel(LocusDev L, const short* __restrict__ configs, long long nu
             k[s]++;
         }
         if (bad) {
-            atomicOr(acc.counters + 1, (unsigned long long)ERR_BAD_CONFIG);
+            flag_set(acc, ERR_BAD_CONFIG);
         } else if (k[0] + k[1] == 0) {                              // postcal.cpp:461-492
             const double einv = 0.36787944117144233;                // exp(-1): "- sqrt(|1|)"
             bin_add(acc, SCAL, S_TOTAL, einv, 0);
@@ -93,14 +93,14 @@ given_configs_kernel(LocusDev L, const short* __restrict__ configs, long long nu
                     if (un[0][i] == un[1][t]) { both0 |= 1 << i; both1 |= 1 << t; a++; }
             const int j = k[0] + k[1] - a;                          // unique union SNPs = numCausal (:516)
             if (j > KMAX) {
-                atomicOr(acc.counters + 1, (unsigned long long)ERR_BAD_CONFIG);
+                flag_set(acc, ERR_BAD_CONFIG);
             } else {
                 bool notpd = false;
                 double m0, m1;
                 int e0, e1;
                 chol_block(L.st[0], loc[0], k[0], m0, e0, notpd);
                 chol_block(L.st[1], loc[1], k[1], m1, e1, notpd);
-                if (notpd) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+                if (notpd) flag_set(acc, ERR_NOT_PD);
                 const double y = m0 * m1, x = y * L.pi[j][a];
                 const int ne = e0 + e1;
                 bin_add(acc, SCAL, S_TOTAL, x, ne);
@@ -122,7 +122,7 @@ given_configs_kernel(LocusDev L, const short* __restrict__ configs, long long nu
     }
     // mycount (:475,619): one atomic per warp
     const unsigned m = __ballot_sync(0xffffffffu, counted != 0);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(acc.counters, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31) == 0 && m) count_add(acc, (unsigned long long)__popc(m));
 }
 
 }  // namespace pipsort

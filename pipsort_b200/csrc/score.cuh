@@ -110,7 +110,7 @@ __device__ inline double score_config(const LocusDev& L, const WarpWS& ws, int k
             bin_add(acc, SCAL, S_TOTAL, einv, 0);
             bin_add(acc, SCAL, S_NC0, einv, 0);
             bin_add(acc, SCAL, S_NC1, einv, 0);
-            atomicAdd(acc.counters, 1ull);
+            count_add(acc, 1ull);
         }
         return L.null_l;
     }
@@ -188,7 +188,7 @@ __device__ inline double score_config(const LocusDev& L, const WarpWS& ws, int k
         ws.f[s * ws.tabn + m] = fv;
         ws.en[s * ws.tabn + m] = en;
     }
-    if (__any_sync(0xffffffffu, notpd) && lane == 0) atomicOr(acc.counters + 1, (unsigned long long)ERR_NOT_PD);
+    if (__any_sync(0xffffffffu, notpd) && lane == 0) flag_set(acc, ERR_NOT_PD);
     __syncwarp();
     // exponent of an absent mask aliases the mask restricted to the SNPs the study has (mantissa stays 0)
     for (int t = lane; t < 2 * (FULL + 1); t += 32) {
@@ -255,7 +255,7 @@ __device__ inline double score_config(const LocusDev& L, const WarpWS& ws, int k
     if (lane == 0) {  // no causal SNP in a study: the other study carries all k (postcal.cpp:988-1000)
         if ((FULL & ~P[0]) == 0) bin_add(acc, SCAL, S_NC1, L.pi[k][0] * em0[FULL], en0[FULL]);
         if ((FULL & ~P[1]) == 0) bin_add(acc, SCAL, S_NC0, L.pi[k][0] * em1[FULL], en1[FULL]);
-        atomicAdd(acc.counters, (u64)nvalid);
+        count_add(acc, (u64)nvalid);
     }
     return best;
 }

@@ -1,0 +1,101 @@
+"""One process per GPU: shard one locus over the ranks of a torch.distributed group.
+
+The configurations of a locus are independent; the only coupling is the final log-sum-exp.  So
+
+* exhaustive (postcal.cpp:716-1092): the union-subset rank space [0, sum_j C(U,j)) is cut into `world`
+  contiguous, work-weighted ranges (pipsort_shard_ranks); LD / z / maps are replicated; every rank runs the same
+  single launch on its range; the accumulator stores -- plain doubles whose element-wise SUM is the accumulator
+  state of the union, configuration count and error counters included -- are combined by ONE all-reduce(sum).
+* stochastic shotgun search (sss_postcal.cpp:223-255): every iteration's list of unseen neighbours is cut into
+  `world` contiguous slices, the per-neighbour scores are all-gathered (the sampling step needs all of them on every
+  rank, sss_postcal.cpp:289-343), the accumulators stay rank-partial until they are read.
+
+Nothing here computes: the engine does (CUDA), torch.distributed moves the small vectors (NCCL on GPUs; the host
+logic is exercised with gloo in tests/test_sharding_cpu.py through an engine stand-in).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world_and_rank(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def bind_engine_to_current_stream(engine):
+    """Make the engine launch on torch's current CUDA stream: the NCCL all-reduce torch enqueues is then ordered
+    after the engine's kernels (and the finalize kernel after the all-reduce) without host synchronisation."""
+    import torch
+    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+
+
+def slice_bounds(n, world):
+    """Contiguous near-equal slices of n items: bounds[r] .. bounds[r+1] belongs to rank r."""
+    return [(n * r) // world for r in range(world + 1)]
+
+
+def run_exhaustive_sharded(engine, c, group=None, bounds=None):
+    """reset + this rank's share of computeTotalLikelihood + ONE all-reduce(sum) of the accumulator store.
+    Asynchronous on the engine's stream; follow with engine.read() (every rank then holds the whole result)."""
+    world, rank = world_and_rank(group)
+    if bounds is None:
+        bounds = engine.shard_ranks(c, world)
+    if len(bounds) != world + 1:
+        raise ValueError("need world+1 shard bounds")
+    engine.reset()
+    engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
+    if world > 1:
+        _dist().all_reduce(engine.accumulator_tensor(), group=group)
+    return bounds
+
+
+def compute_total_likelihood_sharded(engine, c=None, group=None, bounds=None):
+    """PostCal::computeTotalLikelihood (postcal.cpp:716) with the rank space sharded over the group."""
+    c = engine.max_causal if c is None else c
+    run_exhaustive_sharded(engine, c, group, bounds)
+    return engine.read()
+
+
+def score_union_configs_sharded(engine, idx, make_updates=None, group=None):
+    """One SSS neighbourhood (sss_postcal.cpp:223-255) split over the group: rank r scores slice r with accumulator
+    updates, the max-|l| values of all slices are all-gathered.  Returns max_abs_l[n] (identical on every rank)."""
+    world, rank = world_and_rank(group)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    n = idx.shape[0]
+    mu = None if make_updates is None else np.ascontiguousarray(make_updates, dtype=np.uint8)
+    if world == 1:
+        return engine.score_union_configs(idx, mu)
+    import torch
+    b = slice_bounds(n, world)
+    lo, hi = b[rank], b[rank + 1]
+    mine = engine.score_union_configs(idx[lo:hi], None if mu is None else mu[lo:hi]) if hi > lo else np.zeros(0)
+    width = max(b[r + 1] - b[r] for r in range(world))
+    dev = engine.accumulator_tensor().device
+    send = torch.zeros(width, dtype=torch.float64, device=dev)
+    send[:hi - lo] = torch.from_numpy(mine).to(dev)
+    recv = torch.empty(world * width, dtype=torch.float64, device=dev)
+    _dist().all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy().reshape(world, width)
+    return np.concatenate([recv[r, :b[r + 1] - b[r]] for r in range(world)])
+
+
+def read_sharded(engine, group=None):
+    """Results of rank-partial accumulators (after score_union_configs_sharded): all-reduce a COPY of the store so the
+    partial sums can keep accumulating, finalize from the copy, restore."""
+    world, _ = world_and_rank(group)
+    if world == 1:
+        return engine.read()
+    acc = engine.accumulator_tensor()
+    keep = acc.clone()
+    _dist().all_reduce(acc, group=group)
+    res = engine.read()
+    acc.copy_(keep)
+    return res

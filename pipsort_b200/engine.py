@@ -19,6 +19,7 @@ _lib = None
 
 KEEP_ORDER = 1
 GENERIC_ONLY = 2
+RAW_LD = 4
 KMAX = 8
 
 
@@ -33,6 +34,11 @@ class _Locus(C.Structure):
                 ("z", C.POINTER(C.c_double)), ("d", C.POINTER(C.c_double)), ("K", C.c_double),
                 ("union_count", C.c_int32), ("snp_map", C.POINTER(C.c_int32)), ("gamma", C.c_double),
                 ("sharing_param", C.c_double), ("max_causal", C.c_int32)]
+
+
+class _PrepInfo(C.Structure):
+    _fields_ = [("add_diag", C.c_double), ("K", C.c_double), ("min_abs_eig", C.c_double), ("n_negative", C.c_int32),
+                ("psd_iterations", C.c_int32)]
 
 
 class _Outputs(C.Structure):
@@ -50,6 +56,9 @@ def lib():
         L = C.CDLL(path)
         vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
         L.pipsort_create.argtypes = [C.POINTER(_Locus), i32, C.c_uint32, C.POINTER(vp)]
+        L.pipsort_preprocess_study.argtypes = [i32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                               C.POINTER(C.c_double), C.POINTER(_PrepInfo)]
+        L.pipsort_prep_info_get.argtypes = [vp, i32, C.POINTER(_PrepInfo)]
         L.pipsort_destroy.argtypes = [vp]
         L.pipsort_destroy.restype = None
         L.pipsort_reset.argtypes = [vp]
@@ -69,6 +78,7 @@ def lib():
         L.pipsort_accumulator_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.pipsort_merge.argtypes = [vp, vp]
         L.pipsort_shard_ranks.argtypes = [vp, i32, i32, C.POINTER(u64)]
+        L.pipsort_shard_ranks_for_map.argtypes = [C.POINTER(C.c_int32), C.c_int32, i32, i32, C.c_uint32, C.POINTER(u64)]
         L.pipsort_stream.argtypes = [vp]
         L.pipsort_stream.restype = vp
         L.pipsort_sync.argtypes = [vp]
@@ -124,7 +134,7 @@ class Engine:
     """Device-resident locus + accumulators (the hot-path half of the reference's PostCal)."""
 
     def __init__(self, num_snps, sigma, z, d, K, snp_map, gamma=0.01, sharing_param=0.75, max_causal=3, device=0,
-                 keep_order=False, generic_only=False):
+                 keep_order=False, generic_only=False, raw_ld=False):
         self.num_snps = np.ascontiguousarray(num_snps, dtype=np.int32)
         if isinstance(sigma, (list, tuple)):
             sigma = np.concatenate([np.asarray(s, dtype=np.float64).ravel() for s in sigma])
@@ -143,9 +153,16 @@ class Engine:
                      self.U, smap.ctypes.data_as(C.POINTER(C.c_int32)), float(gamma), float(sharing_param),
                      int(max_causal))
         self._h = C.c_void_p()
-        _check(lib().pipsort_create(C.byref(loc), int(device), (KEEP_ORDER if keep_order else 0) | (GENERIC_ONLY if generic_only else 0), C.byref(self._h)))
+        _check(lib().pipsort_create(C.byref(loc), int(device), (KEEP_ORDER if keep_order else 0) | (GENERIC_ONLY if generic_only else 0) | (RAW_LD if raw_ld else 0),
+                                    C.byref(self._h)))
         self.max_causal = int(max_causal)
         self.device = int(device)
+
+    def prep_info(self, study):
+        """What the on-device pre-processing found (engines created with raw_ld=True): dict of pipsort_prep_info."""
+        info = _PrepInfo()
+        _check(lib().pipsort_prep_info_get(self._h, int(study), C.byref(info)))
+        return {k: getattr(info, k) for k, _ in _PrepInfo._fields_}
 
     # -- lifetime ------------------------------------------------------------------------------------
     def close(self):
@@ -302,6 +319,27 @@ class Engine:
 
     def launch_count(self):
         return int(lib().pipsort_launch_count(self._h))
+
+
+def preprocess_study(ld, z, device=0):
+    """Model's per-study pre-processing (model.h:171-264) on the GPU: returns (sigma_eff, info dict)."""
+    ld = np.ascontiguousarray(ld, dtype=np.float64)
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    n = ld.shape[0]
+    assert ld.shape == (n, n) and z.shape == (n,)
+    out = np.empty((n, n))
+    info = _PrepInfo()
+    _check(lib().pipsort_preprocess_study(int(device), n, _dp(ld), _dp(z), _dp(out), C.byref(info)))
+    return out, {k: getattr(info, k) for k, _ in _PrepInfo._fields_}
+
+
+def shard_ranks_for_map(snp_map, c, parts, keep_order=False):
+    """pipsort_shard_ranks without an engine (pure host arithmetic, no device needed)."""
+    smap = np.ascontiguousarray(snp_map, dtype=np.int32)
+    b = (C.c_uint64 * (parts + 1))()
+    _check(lib().pipsort_shard_ranks_for_map(smap.ctypes.data_as(C.POINTER(C.c_int32)), int(smap.shape[1]), int(c),
+                                             int(parts), KEEP_ORDER if keep_order else 0, b))
+    return [int(x) for x in b]
 
 
 def measure_fp64_peak(device=0):

@@ -53,7 +53,22 @@ Model::Model(const std::vector<std::string>& ldDir, const std::vector<std::strin
     double K = 0.0;
     for (int i = 0; i < num_of_studies; i++) {
         const auto t0 = std::chrono::steady_clock::now();
-        const Prep p = preprocess_study(sigma[i], z_score[i], num_snps_all[i]);
+        // model.h:171-264 on the GPU (cuSOLVER LU / eigensolver + the engine's kernels); PIPSORT_HOST_PREP=1 keeps the
+        // host restatement (O(n^3) Jacobi sweeps: fine for hundreds of SNPs, hopeless for thousands)
+        Prep p;
+        const char* hp = std::getenv("PIPSORT_HOST_PREP");
+        if (hp && *hp == '1') {
+            p = preprocess_study(sigma[i], z_score[i], num_snps_all[i]);
+        } else {
+            pipsort_prep_info info;
+            std::vector<double> eff(sigma[i].size());
+            if (pipsort_preprocess_study(device, num_snps_all[i], sigma[i].data(), z_score[i].data(), eff.data(), &info) != 0) {
+                std::cout << pipsort_last_error() << std::endl;
+                std::exit(1);
+            }
+            sigma[i].swap(eff);
+            p.add_diag = info.add_diag; p.K = info.K; p.min_eig = info.min_abs_eig;
+        }
         const auto t1 = std::chrono::steady_clock::now();
         std::cout << "Time to make psd + eigen decomp = " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count()
                   << "[µs] (diagonal shift " << p.add_diag << ", smallest eigenvalue " << p.min_eig << ")" << std::endl;
