@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="B150c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "allreduce"],
+                    help="multi-GPU combine step: the engine's peer-memory kernels (default) or one NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sat", action="store_true", help="skip the saturating B1500c3 side measurement")
     args = ap.parse_args()
@@ -268,6 +270,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    collective_used = []
+
     def measure(L, c, steps, warmup, clocks=False):
         """Device-timed steps on the resident locus; returns dict of timings."""
         total_configs = synth.count_configs(L.snp_map, c)
@@ -276,9 +280,15 @@ def main():
         stream = torch.cuda.current_stream()
         e.set_stream(stream.cuda_stream)
         b = e.shard_ranks(c, world)
+        # combine step: the engine's own peer-memory kernels over NVLink (CUDA IPC mailboxes) when the ranks can map each
+        # other, else ONE NCCL all-reduce(sum) of the accumulator store
+        coll = "allreduce"
+        if world > 1 and args.collective != "allreduce":
+            coll = "p2p" if D.connect_p2p(e) else "allreduce"
+        collective_used.append(coll)
 
         def step():
-            D.run_exhaustive_sharded(e, c, bounds=b)   # reset + this rank's launch + ONE NCCL all-reduce(sum) of the store
+            D.run_exhaustive_sharded(e, c, bounds=b, collective=coll)   # reset + this rank's launch + the combine step
             e.finalize()
 
         for _ in range(warmup):
@@ -307,13 +317,16 @@ def main():
         kms = [k for k in kms if k is not None]
         tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
         k_ms = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
-        cnt = e.config_count()            # the count rides in the all-reduced store: the whole job's on every rank
+        cnt = e.config_count()            # the count rides in the combined store: the whole job's (on the root at least)
         if world > 1:
             dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
         res = e.read() if rank == 0 else None
+        if world > 1:
+            dist.barrier()
         e.close()
-        assert cnt == total_configs, (cnt, total_configs)
+        if rank == 0:
+            assert cnt == total_configs, (cnt, total_configs)
         return dict(total_configs=total_configs, ms_per_step=float(tot_ms.item()) / steps, kernel_ms=float(k_ms.item()),
                     launches=launches, wall_ms_per_step=1e3 * t_wall / steps, clocks=clk, result=res)
 
@@ -380,8 +393,11 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl_desc(args.workload, L, c), "configs_per_step": main_m["total_configs"],
                            "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                           "sharding": f"rank space split into {world} work-weighted contiguous ranges, one NCCL all-reduce(sum) "
-                                       "of the accumulator store per step" if world > 1 else "single GPU"},
+                           "sharding": (f"rank space split into {world} work-weighted contiguous ranges; combine step per step: "
+                                        + ("non-root ranks add their non-zero accumulator bins into the root's memory over NVLink "
+                                           "(engine kernels, CUDA IPC peer memory, device-side arrival words)"
+                                           if collective_used and collective_used[0] == "p2p" else
+                                           "one NCCL all-reduce(sum) of the accumulator store")) if world > 1 else "single GPU"},
                 "clocks": main_m["clocks"], "e2e": e2e, "gpu_launches": main_m["launches"], "roofline": roof,
                 "locus_wall_ms": e2e["ms_per_step"], "wall_ms_per_step": main_m["wall_ms_per_step"]}
         if cpu is not None:

@@ -143,6 +143,19 @@ int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, 
 int pipsort_score_given_configs(pipsort_engine* e, const int16_t* configs, int64_t num_configs, int num_groups);
 int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_configs, int64_t num_configs, int num_groups);
 
+/* Replaces PostCal::sss_computeTotalLikelihood (sss_postcal.cpp:102-380): the whole stochastic shotgun search from the
+ * empty configuration -- std::mt19937(12345), at most max_iterations (the reference: 1000) rounds of
+ * zero ++ minus ++ plus neighbourhoods (sss_postcal.cpp:20-99), every unseen neighbour expanded + scored +
+ * accumulated in ONE launch, the three within-group std::discrete_distribution draws and the draw across groups
+ * (sss_postcal.cpp:289-343), the "no new configuration" break (:260-263) and the 1e-3 convergence rule after 100
+ * rounds (:265-270).  The explored-configuration map (PostCal::config_hashmap, postcal.h:98) is a hash table in device
+ * memory; per round only the current configuration goes to the device and the neighbours' values come back.
+ * Accumulates into the engine's accumulators (call pipsort_reset first for a fresh PostCal); *iterations receives the
+ * number of completed rounds, *stop_reason 0 = max_iterations reached, 1 = break condition, 2 = convergence.     */
+int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* iterations, int32_t* stop_reason);
+/* Forget the explored configurations (pipsort_sss does this itself when it starts). */
+int pipsort_sss_reset(pipsort_engine* e);
+
 /* Reads the accumulators into PostCal's result arrays (any member of `out` may be NULL).  Replaces the
  * reads of totalLikeLihoodLOG / postValues / noCausal / sharedPips / sharedLL / notSharedLL by
  * findOptimalSetGreedy (postcal.cpp:1144-1163) and printPost2File (postcal.h:288-336).            */
@@ -159,6 +172,10 @@ int pipsort_last_kernel_ms(pipsort_engine* e, float* ms);
 /* Number of expanded configurations accumulated since the last reset (the reference's mycount). */
 int pipsort_config_count(pipsort_engine* e, uint64_t* out);
 
+/* The same count as it was when pipsort_read_accumulators last ran (it travels with the results: no extra device
+ * round trip).                                                                                     */
+int pipsort_last_read_config_count(const pipsort_engine* e, uint64_t* out);
+
 /* Debug / parity: the configuration the reference evaluates at union-subset rank `rank`, expansion
  * number `expansion` (ascending bmask order with checkOR rejects skipped, postcal.cpp:903-958), in
  * snp_map order regardless of the engine's internal relabelling.  out_union_idx[c] gets the chosen
@@ -174,6 +191,19 @@ int pipsort_enumerate(pipsort_engine* e, int c, uint64_t rank, uint32_t expansio
  * this buffer; a single process driving several devices can use pipsort_merge.                    */
 int pipsort_accumulator_buffer(pipsort_engine* e, void** device_ptr, uint64_t* num_doubles);
 int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copies across devices)  */
+
+/* The same combine step WITHOUT a collective library, over NVLink / NVSwitch peer memory (one process per GPU):
+ * every engine exports a mailbox (CUDA IPC handle, PIPSORT_IPC_HANDLE_BYTES bytes), the launcher exchanges the handles
+ * (any side channel: torch.distributed all_gather_object, MPI, a file) and hands every rank the whole table.  After that
+ * pipsort_p2p_reduce_to_root -- stream-ordered, asynchronous, called by EVERY rank after its pipsort_run_exhaustive
+ * / scoring calls -- makes the non-root ranks add the non-zero entries of their accumulator stores straight into the
+ * root's memory with system-scope fp64 atomics and makes the root wait (on the device) for all of them and fold them
+ * into its store: pipsort_read_accumulators on the ROOT then returns the whole job's result.  Engines of one group must
+ * be created from the same locus and call in lockstep (the n-th call of every rank belongs together).            */
+#define PIPSORT_IPC_HANDLE_BYTES 64
+int pipsort_p2p_export(pipsort_engine* e, void* handle);
+int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int rank, int root);
+int pipsort_p2p_reduce_to_root(pipsort_engine* e);
 
 /* Split [0,total) into `parts` contiguous rank ranges of roughly equal work (expanded configurations
  * weighted); bounds receives parts+1 values.                                                      */

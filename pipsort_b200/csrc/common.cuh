@@ -65,7 +65,7 @@ struct AccDev {
                        // mycount; exact below 2^53), [1 + f] number of times error f was raised.  Doubles, so that the
                        // ONE all-reduce(sum) that combines the stores of several GPUs carries them as well.
 };
-enum ErrFlag : int { ERR_RANGE = 0, ERR_NOT_PD = 1, ERR_BAD_CONFIG = 2, NERRFLAG = 3 };
+enum ErrFlag : int { ERR_RANGE = 0, ERR_NOT_PD = 1, ERR_BAD_CONFIG = 2, ERR_P2P_TIMEOUT = 3, NERRFLAG = 4 };
 constexpr int NCOUNTER = 1 + NERRFLAG;
 
 struct LocusDev {

@@ -8,6 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <numeric>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -16,6 +19,8 @@
 #include "exhaustive.cuh"
 #include "given.cuh"
 #include "prep.cuh"
+#include "sss.cuh"
+#include "p2p.cuh"
 #include "score.cuh"
 
 using namespace pipsort;
@@ -116,6 +121,7 @@ constexpr int FIN_WARPS = 8;
 __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res) {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x < NCOUNTER) res[3 + (size_t)5 * U + threadIdx.x] = acc.counters[threadIdx.x];
     if (w < 3) {
         const XAcc v = bins_read_warp(acc, SCAL, w, lane);
         if (lane == 0) res[w] = xlog_or_zero(v, cx);
@@ -163,9 +169,9 @@ struct pipsort_engine {
     int device = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     void* l2_scratch = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_up = nullptr;
     bool evk_valid = false;
-    LocusDev L;
+    LocusDev L, L_host_copy;
     LocusDev* d_L = nullptr;        // device copy (the slow path of the register kernel reads it by pointer)
     int U = 0, kb = 3, sm_count = 148;
     int n_raw[2] = {0, 0};
@@ -186,6 +192,26 @@ struct pipsort_engine {
     int score_smem_set = 0;
     ExhScratch exh;
     bool use_reg_kernel = true;
+    uint64_t last_read_count = 0;   // configuration count seen by the last pipsort_read_accumulators
+    // stochastic shotgun search state (pipsort_sss): explored-configuration hash table + per-iteration buffers
+    struct Sss {
+        SssTable tab{nullptr, nullptr, nullptr, 0};
+        u64 count = 0;              // entries in the table
+        double* d_out_l = nullptr; int* d_batch = nullptr; unsigned char* d_upd = nullptr; int* d_unseen = nullptr;
+        int* d_counter = nullptr; double* d_scored = nullptr;
+        double* h_out_l = nullptr;  // pinned: [n_max] neighbour values + 1 slot reused for the counter
+        long long n_max = 0; int kmax = 0;
+    } sss;
+    // peer-memory combine (p2p.cuh): this rank's mailbox + the peers' mapped mailboxes
+    struct P2P {
+        double* mailbox = nullptr;   // [bins_len] inbox | 8 control words
+        unsigned* d_done = nullptr;
+        void* peer_base[P2P_MAX_WORLD] = {nullptr};
+        P2PPeers peers;
+        int world = 0, rank = 0, root = 0;
+        u64 epoch = 0;
+        bool connected = false;
+    } p2p;
     PrepResult prep[2];             // PIPSORT_RAW_LD: what the on-device pre-processing found per study
     bool prepped = false;
 };
@@ -195,6 +221,31 @@ namespace {
 // Stream-ordered allocation from the device's default memory pool: after the first engine on a device the
 // pool serves create/destroy without touching the driver allocator (the locus arrays of a fine-mapping run
 // are created and destroyed once per locus).
+// Streams and timing events are recycled across engines of one process (a fine-mapping run creates and destroys one
+// engine per locus; cudaStreamCreate / cudaEventCreate are a measurable part of a 0.1 ms locus).
+struct StreamKit { cudaStream_t stream; cudaEvent_t ev[5]; };
+std::vector<StreamKit>& kit_cache(int device) {
+    static std::vector<StreamKit> cache[64];
+    return cache[device & 63];
+}
+std::mutex& kit_mutex() { static std::mutex m; return m; }
+
+int kit_acquire(int device, StreamKit* k) {
+    {
+        std::lock_guard<std::mutex> g(kit_mutex());
+        auto& c = kit_cache(device);
+        if (!c.empty()) { *k = c.back(); c.pop_back(); return 0; }
+    }
+    CU(cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CU(cudaEventCreate(&k->ev[i]));
+    CU(cudaEventCreateWithFlags(&k->ev[4], cudaEventDisableTiming));
+    return 0;
+}
+void kit_release(int device, const StreamKit& k) {
+    std::lock_guard<std::mutex> g(kit_mutex());
+    kit_cache(device).push_back(k);
+}
+
 int pool_setup(int device) {
     static bool done[64] = {false};
     if (device < 64 && done[device]) return 0;
@@ -265,16 +316,35 @@ void pipsort_destroy(pipsort_engine* e) {
     if (e->own_stream) {
         if (e->exh.d_prefix) cudaFreeAsync(e->exh.d_prefix, e->own_stream);
         if (e->exh.d_counter) cudaFreeAsync(e->exh.d_counter, e->own_stream);
-        for (void* p : e->allocs) cudaFreeAsync(p, e->own_stream);
-        cudaStreamSynchronize(e->own_stream);
+        for (void* p : e->allocs) cudaFreeAsync(p, e->own_stream);   // stream-ordered: no second synchronisation needed
+    }
+    {
+        pipsort_engine::Sss& q = e->sss;
+        void* ps[] = {q.tab.klo, q.tab.khi, q.tab.val, q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored};
+        for (void* p : ps) if (p) cudaFree(p);
+        if (q.h_out_l) cudaFreeHost(q.h_out_l);
+    }
+    {
+        pipsort_engine::P2P& q = e->p2p;
+        for (int r = 0; r < P2P_MAX_WORLD; r++) if (q.peer_base[r] && r != q.rank) cudaIpcCloseMemHandle(q.peer_base[r]);
+        if (q.mailbox) cudaFree(q.mailbox);
+        if (q.d_done) cudaFree(q.d_done);
     }
     if (e->d_idx) cudaFree(e->d_idx);
     if (e->d_upd) cudaFree(e->d_upd);
     if (e->d_out) cudaFree(e->d_out);
+    if (e->own_stream && e->ev0 && e->ev1 && e->evk0 && e->evk1 && e->ev_up) {   // back to the per-device cache
+        StreamKit k{e->own_stream, {e->ev0, e->ev1, e->evk0, e->evk1, e->ev_up}};
+        if (e->l2_scratch) cudaFree(e->l2_scratch);
+        kit_release(e->device, k);
+        delete e;
+        return;
+    }
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->evk0) cudaEventDestroy(e->evk0);
     if (e->evk1) cudaEventDestroy(e->evk1);
+    if (e->ev_up) cudaEventDestroy(e->ev_up);
     if (e->l2_scratch) cudaFree(e->l2_scratch);
 
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -294,12 +364,13 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         int rcp = pool_setup(device);
         if (rcp) return rcp;
     }
-    CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    {
+        StreamKit k;
+        int rck = kit_acquire(device, &k);
+        if (rck) return rck;
+        e->own_stream = k.stream; e->ev0 = k.ev[0]; e->ev1 = k.ev[1]; e->evk0 = k.ev[2]; e->evk1 = k.ev[3]; e->ev_up = k.ev[4];
+    }
     e->stream = e->own_stream;
-    CU(cudaEventCreate(&e->ev0));
-    CU(cudaEventCreate(&e->ev1));
-    CU(cudaEventCreate(&e->evk0));
-    CU(cudaEventCreate(&e->evk1));
     e->U = U;
     e->K = lc->K; e->gamma = lc->gamma; e->p = lc->sharing_param;
     e->kb = std::min(KMAX, std::max(3, lc->max_causal));
@@ -344,8 +415,8 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     //   u2i[U] | snp_map[2U] | loc0[U] | loc1[U] | orig0 | orig1 | raw2loc0 | raw2loc1 | loc2u0 | loc2u1
     int* d_ints = nullptr;
     size_t orig_off[2], r2l_off[2], l2u_off[2];
+    std::vector<int> pack;   // function scope: stays alive until the uploads have completed (ev_up below)
     {
-        std::vector<int> pack;
         pack.reserve((size_t)5 * U + 2 * (e->orig[0].size() + e->orig[1].size()) + lc->num_snps[0] + lc->num_snps[1]);
         pack.insert(pack.end(), u2i.begin(), u2i.end());
         pack.insert(pack.end(), lc->snp_map, lc->snp_map + (size_t)2 * U);
@@ -371,6 +442,19 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     size_t soff = 0, zoff = 0;
     double maxexp_nats = 0.0, minexp_bits = 0.0;
     double K_total = (flags & PIPSORT_RAW_LD) ? 0.0 : lc->K;
+    // all host -> device copies of the caller's buffers first, then one event: pipsort_create returns when they are done
+    double *up_sigma[2] = {nullptr, nullptr}, *up_z[2] = {nullptr, nullptr};
+    {
+        size_t so = 0, zo = 0;
+        for (int s = 0; s < S; s++) {
+            const size_t nr = (size_t)lc->num_snps[s];
+            CU(cudaMallocAsync(&up_sigma[s], std::max<size_t>(nr * nr, 1) * sizeof(double), e->stream));
+            CU(cudaMemcpyAsync(up_sigma[s], lc->sigma + so, nr * nr * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            if ((rc = dev_upload(e, &up_z[s], lc->z + zo, nr))) return rc;
+            so += nr * nr; zo += nr;
+        }
+        CU(cudaEventRecord(e->ev_up, e->stream));
+    }
     for (int s = 0; s < S; s++) {
         const int n_raw = lc->num_snps[s], n = (int)e->orig[s].size();
         const int ldw = (n + 3) & ~3;
@@ -379,9 +463,8 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         double *d_sigma = nullptr, *d_zraw = nullptr, *W = nullptr, *A = nullptr, *z = nullptr, *invA = nullptr, *u = nullptr,
                *e1m = nullptr;
         int *d_orig = nullptr, *d_loc = nullptr, *e1n = nullptr;
-        CU(cudaMallocAsync(&d_sigma, std::max<size_t>((size_t)n_raw * n_raw, 1) * sizeof(double), e->stream));
-        CU(cudaMemcpyAsync(d_sigma, lc->sigma + soff, (size_t)n_raw * n_raw * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        if ((rc = dev_upload(e, &d_zraw, lc->z + zoff, n_raw))) return rc;
+        d_sigma = up_sigma[s];
+        d_zraw = up_z[s];
         if (flags & PIPSORT_RAW_LD) {   // model.h:171-264 on the device: PSD shift + eigen-decomposition -> effective LD, K_s
             std::string why;
             const int prc = prep_study_device(e->stream, n_raw, d_sigma, d_zraw, &e->prep[s], &why, &e->launches);
@@ -493,11 +576,15 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->bins_len = (size_t)NSLOT * acc.NB * acc.Upad + NCOUNTER;   // the counters ride in the tail of the store
     if ((rc = dev_alloc(e, &acc.bins, e->bins_len))) return rc;
     acc.counters = acc.bins + (e->bins_len - NCOUNTER);
-    if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U))) return rc;
-    e->h_res.resize(3 + (size_t)5 * U);
+    if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U + NCOUNTER))) return rc;   // results | counters: one D2H per read
+    e->h_res.resize(3 + (size_t)5 * U + NCOUNTER);
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
-    if ((rc = dev_upload(e, &e->d_L, &e->L, 1))) return rc;
-    CU(cudaStreamSynchronize(e->stream));
+    // the caller's buffers and the local staging vectors must not be read after return: wait for the H2D copies only
+    // (recorded in ev_up after the last of them); the preparation kernels and memsets keep running asynchronously.
+    // e->L lives as long as the engine, so its upload needs no wait.
+    e->L_host_copy = e->L;
+    if ((rc = dev_upload(e, &e->d_L, &e->L_host_copy, 1))) return rc;
+    CU(cudaEventSynchronize(e->ev_up));
     return 0;
 }
 
@@ -640,7 +727,7 @@ int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, 
     int rc = ensure_score_smem(e, wk, &smem);
     if (rc) return rc;
     const int blocks = (int)std::min<int64_t>((n + SCORE_WARPS - 1) / SCORE_WARPS, (int64_t)e->sm_count * 8);
-    score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, d_idx, n, kmax, wk, d_make_updates, d_out);
+    score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, d_idx, n, kmax, wk, d_make_updates, d_out, nullptr);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -681,6 +768,136 @@ int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_confi
 }
 
 static int check_flags(pipsort_engine* e);
+static int flags_to_error(const double* counters);
+
+// ---- stochastic shotgun search -----------------------------------------------------------------------------
+static int sss_table_alloc(SssTable* t, u64 cap, cudaStream_t st) {
+    t->mask = cap - 1;
+    CU(cudaMalloc(&t->klo, cap * sizeof(u64)));
+    CU(cudaMalloc(&t->khi, cap * sizeof(u64)));
+    CU(cudaMalloc(&t->val, cap * sizeof(double)));
+    CU(cudaMemsetAsync(t->khi, 0, cap * sizeof(u64), st));
+    return 0;
+}
+
+static int sss_table_reserve(pipsort_engine* e, u64 need) {   // capacity >= 2 * need
+    pipsort_engine::Sss& q = e->sss;
+    u64 cap = q.tab.khi ? q.tab.mask + 1 : 0;
+    if (cap >= 2 * need && cap) return 0;
+    u64 ncap = std::max<u64>(cap, 1u << 16);
+    while (ncap < 2 * need) ncap <<= 1;
+    SssTable nt{nullptr, nullptr, nullptr, 0};
+    int rc = sss_table_alloc(&nt, ncap, e->stream);
+    if (rc) return rc;
+    if (q.tab.khi) {
+        sss_rehash_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, e->stream>>>(q.tab, nt);
+        e->launches++;
+        CU(cudaStreamSynchronize(e->stream));
+        cudaFree(q.tab.klo); cudaFree(q.tab.khi); cudaFree(q.tab.val);
+    }
+    q.tab = nt;
+    return 0;
+}
+
+int pipsort_sss_reset(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    pipsort_engine::Sss& q = e->sss;
+    if (q.tab.khi) CU(cudaMemsetAsync(q.tab.khi, 0, (q.tab.mask + 1) * sizeof(u64), e->stream));
+    q.count = 0;
+    return 0;
+}
+
+int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* iterations, int32_t* stop_reason) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    const int c = max_causal, U = e->U;
+    if (c < 0 || c > e->kb) return fail(PIPSORT_E_ARG, "max_causal=%d outside [0,%d] (max_causal given at create)", c, e->kb);
+    if (U > SSS_MAX_U) return fail(PIPSORT_E_RANGE, "the search state packs union indices into 15 bits: U=%d > %d", U, SSS_MAX_U);
+    if (max_iterations < 0) return fail(PIPSORT_E_ARG, "negative iteration count");
+    CU(cudaSetDevice(e->device));
+    pipsort_engine::Sss& q = e->sss;
+    const int kmax = std::max(c, 1);
+    const long long n_max = (long long)U * std::max(c, 1) + c + U + 1;
+    if (q.n_max < n_max || q.kmax != kmax) {
+        void* ps[] = {q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored};
+        for (void* p : ps) if (p) cudaFree(p);
+        if (q.h_out_l) cudaFreeHost(q.h_out_l);
+        q.h_out_l = nullptr;
+        CU(cudaMalloc(&q.d_out_l, (size_t)(n_max + 1) * sizeof(double)));
+        CU(cudaMalloc(&q.d_batch, (size_t)(n_max + 1) * kmax * sizeof(int)));
+        CU(cudaMalloc(&q.d_upd, (size_t)(n_max + 1)));
+        CU(cudaMalloc(&q.d_unseen, (size_t)n_max * sizeof(int)));
+        CU(cudaMalloc(&q.d_counter, sizeof(int)));
+        CU(cudaMalloc(&q.d_scored, (size_t)(n_max + 1) * sizeof(double)));
+        CU(cudaMallocHost(&q.h_out_l, (size_t)(n_max + 1) * sizeof(double)));
+        q.n_max = n_max; q.kmax = kmax;
+    }
+    int rc = pipsort_sss_reset(e);
+    if (rc) return rc;
+    size_t smem = 0;
+    if ((rc = ensure_score_smem(e, kmax, &smem))) return rc;
+
+    std::mt19937 gen(12345);                                             // sss_postcal.cpp:138
+    SssCur cur;
+    memset(&cur, 0, sizeof cur);                                         // causal_locs starts empty (:115)
+    double old_sum_lkl = 0, sss_sum_lkl = 0;
+    int iter = 0, why = 0;
+    std::vector<double> probs;
+    for (iter = 0; iter < max_iterations; iter++) {
+        long long nz, nm, np;
+        sss_nbd_sizes(U, cur.k, c, nz, nm, np);
+        const long long n = nz + nm + np;
+        if ((rc = sss_table_reserve(e, q.count + (u64)n))) return rc;
+        CU(cudaMemsetAsync(q.d_counter, 0, sizeof(int), e->stream));
+        sss_lookup_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, e->stream>>>(q.tab, cur, U, c, n, kmax, q.d_out_l, q.d_batch,
+                                                                                 q.d_upd, q.d_unseen, q.d_counter);
+        // one launch scores the current configuration + every unseen neighbour (the batch length is read on the device)
+        const int blocks = (int)std::min<long long>((n + 1 + SCORE_WARPS - 1) / SCORE_WARPS, (long long)e->sm_count * 8);
+        score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, q.d_batch, 1, kmax, kmax, q.d_upd, q.d_scored, q.d_counter);
+        sss_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(q.tab, q.d_batch, kmax, q.d_scored, q.d_unseen, q.d_counter,
+                                                                             q.d_out_l);
+        e->launches += 3;
+        CU(cudaGetLastError());
+        int n_new = 0;
+        CU(cudaMemcpyAsync(&n_new, q.d_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        if (n > 0) CU(cudaMemcpyAsync(q.h_out_l, q.d_out_l, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (n_new == 0) { why = 1; break; }                              // "hit break condition", :260-263
+        // (the reference inserts the new values after this check and the next one; the table already holds them, which
+        //  is unobservable: both exits leave the loop)
+        q.count += (u64)n_new;
+        if (iter >= 99) {                                                // the running sum is only consulted from here on
+            pipsort_outputs o = {&sss_sum_lkl, nullptr, nullptr, nullptr, nullptr, nullptr};
+            if ((rc = pipsort_read_accumulators(e, &o))) return rc;
+        }
+        if (iter >= 100 && (1 - std::exp(old_sum_lkl - sss_sum_lkl)) <= 0.001) { why = 2; break; }   // :265-270
+
+        // sampling, sss_postcal.cpp:289-343: one draw inside each group, then one across the groups
+        const double* ll = q.h_out_l;
+        double weight[3] = {0.0, 0.0, 0.0};
+        long long sample[3] = {n, n, n};
+        const long long lo[3] = {0, nz, nz + nm}, hi[3] = {nz, nz + nm, n};
+        for (int g = 0; g < 3; g++) {
+            if (lo[g] == hi[g]) continue;
+            const double max_log = *std::max_element(ll + lo[g], ll + hi[g]);
+            probs.clear();
+            for (long long ii = lo[g]; ii < hi[g]; ii++) probs.push_back(std::exp(ll[ii] - max_log));
+            std::discrete_distribution<size_t> dist(probs.begin(), probs.end());
+            sample[g] = (long long)dist(gen);
+            weight[g] = std::accumulate(probs.begin(), probs.end(), 0.0);
+        }
+        std::discrete_distribution<size_t> dist({weight[0], weight[1], weight[2]});
+        const size_t grp = dist(gen);
+        SssCur nxt;
+        memset(&nxt, 0, sizeof nxt);
+        nxt.k = sss_neighbour(cur, U, c, sample[grp] + lo[grp], nxt.g);  // :354
+        cur = nxt;
+        old_sum_lkl = sss_sum_lkl;
+    }
+    if (iterations) *iterations = iter;
+    if (stop_reason) *stop_reason = why;
+    return check_flags(e);
+}
 
 int pipsort_score_given_configs(pipsort_engine* e, const int16_t* configs, int64_t num_configs, int num_groups) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
@@ -723,9 +940,14 @@ static int check_flags(pipsort_engine* e) {
     double c[NCOUNTER];
     CU(cudaMemcpyAsync(c, e->L.acc.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    return flags_to_error(c);
+}
+
+static int flags_to_error(const double* c) {
     if (c[1 + ERR_NOT_PD] != 0.0) return fail(PIPSORT_E_SINGULAR, "matrix is singular");   // postcal.cpp:291-294
     if (c[1 + ERR_RANGE] != 0.0) return fail(PIPSORT_E_RANGE, "a contribution fell outside the provisioned exponent range");
     if (c[1 + ERR_BAD_CONFIG] != 0.0) return fail(PIPSORT_E_CONFIG, "This did not work as expected");   // postcal.cpp:593-596
+    if (c[1 + ERR_P2P_TIMEOUT] != 0.0) return fail(PIPSORT_E_CUDA, "a peer did not arrive at the accumulator combine step in time");
     return 0;
 }
 
@@ -755,8 +977,10 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
     if (rcf) return rcf;
     const int U = e->U;
     CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    int rc = check_flags(e);
+    CU(cudaStreamSynchronize(e->stream));
+    int rc = flags_to_error(e->h_res.data() + 3 + (size_t)5 * U);
     if (rc) return rc;
+    e->last_read_count = (uint64_t)e->h_res[3 + (size_t)5 * U];
     const double* r = e->h_res.data();
     if (out->total) *out->total = r[0];
     if (out->noCausal) { out->noCausal[0] = r[1]; out->noCausal[1] = r[2]; }
@@ -777,6 +1001,12 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
         if (out->sharedLL) out->sharedLL[ug] = r[(size_t)3 * U + g];
         if (out->notSharedLL) out->notSharedLL[ug] = r[(size_t)4 * U + g];
     }
+    return 0;
+}
+
+int pipsort_last_read_config_count(const pipsort_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    *out = e->last_read_count;
     return 0;
 }
 
@@ -843,6 +1073,72 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
 }
 
 static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds);
+
+// ---- peer-memory combine -----------------------------------------------------------------------------------
+int pipsort_p2p_export(pipsort_engine* e, void* handle) {
+    if (!e || !handle) return fail(PIPSORT_E_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    pipsort_engine::P2P& q = e->p2p;
+    if (!q.mailbox) {
+        const size_t bytes = (e->bins_len + 8) * sizeof(double);
+        CU(cudaMalloc(&q.mailbox, bytes));                       // cudaMalloc (not the pool): CUDA IPC needs it
+        CU(cudaMemset(q.mailbox, 0, bytes));
+        CU(cudaMalloc(&q.d_done, sizeof(unsigned)));
+        CU(cudaMemset(q.d_done, 0, sizeof(unsigned)));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, q.mailbox));
+    static_assert(sizeof(cudaIpcMemHandle_t) == PIPSORT_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle, &h, sizeof h);
+    return 0;
+}
+
+int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int rank, int root) {
+    if (!e || !handles) return fail(PIPSORT_E_ARG, "null argument");
+    if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || root < 0 || root >= world)
+        return fail(PIPSORT_E_ARG, "bad world/rank/root (%d/%d/%d)", world, rank, root);
+    pipsort_engine::P2P& q = e->p2p;
+    if (!q.mailbox) return fail(PIPSORT_E_ARG, "call pipsort_p2p_export first");
+    if (q.connected) return fail(PIPSORT_E_ARG, "already connected");
+    CU(cudaSetDevice(e->device));
+    q.world = world; q.rank = rank; q.root = root;
+    q.peers.world = world; q.peers.root = root;
+    for (int r = 0; r < world; r++) {
+        void* base = q.mailbox;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)handles + (size_t)r * PIPSORT_IPC_HANDLE_BYTES, sizeof h);
+            CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        q.peer_base[r] = base;
+        q.peers.ctrl[r] = reinterpret_cast<u64*>(static_cast<double*>(base) + e->bins_len);
+    }
+    q.epoch = 0;
+    q.connected = true;
+    return 0;
+}
+
+int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    pipsort_engine::P2P& q = e->p2p;
+    if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
+    if (q.world == 1) return 0;
+    CU(cudaSetDevice(e->device));
+    q.epoch++;
+    const size_t n = e->bins_len;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)e->sm_count * 2);
+    double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
+    if (q.rank != q.root) {
+        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<double*>(q.peer_base[q.root]), q.peers.ctrl[q.root],
+                                                       q.peers.ctrl[q.rank], q.epoch, q.d_done, errf);
+    } else {
+        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, q.peers.ctrl[q.rank],
+                                                        q.epoch * (u64)(q.world - 1), q.epoch, q.peers, q.rank, q.d_done, errf);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
 
 int pipsort_shard_ranks(const pipsort_engine* e, int c, int parts, uint64_t* bounds) {
     if (!e || !bounds || parts < 1) return fail(PIPSORT_E_ARG, "bad argument");

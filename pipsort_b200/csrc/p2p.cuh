@@ -1,0 +1,88 @@
+// The multi-GPU combine step over NVLink / NVSwitch peer memory -- instead of an NCCL all-reduce.
+//
+// One process per GPU.  Every engine owns a MAILBOX in device memory (cudaMalloc + CUDA IPC handle, mapped by every
+// peer): an inbox with the layout of the accumulator store plus two control words.  After a rank's exhaustive launch
+//   non-root:  p2p_push_kernel  adds the NON-ZERO entries of its store straight into the root's inbox with system-scope
+//              fp64 atomics that travel over NVLink (the store is sparse: a few bins per accumulator are ever touched),
+//              fences, and bumps the root's `arrivals` word;
+//   root:      p2p_merge_kernel polls its LOCAL `arrivals` word until all peers of this epoch have arrived, folds the inbox
+//              into its store, clears it, and writes `consumed = epoch` into every peer's control word (flow control: a
+//              peer may only push epoch k once the root has cleared the inbox of epoch k-1; peers poll their LOCAL word).
+// Both are ordinary stream-ordered launches: no host synchronisation, no collective library, and the only data that
+// crosses the links are the non-zero accumulator bins.  Spins are bounded (a few seconds of clock64) and raise
+// ERR_P2P_TIMEOUT instead of hanging the device.
+#pragma once
+#include "common.cuh"
+
+namespace pipsort {
+
+typedef unsigned long long u64;
+
+constexpr int P2P_MAX_WORLD = 16;
+constexpr long long P2P_SPIN_CYCLES = 6000000000ll;   // ~3 s at 1.9 GHz
+
+struct P2PPeers {
+    u64* ctrl[P2P_MAX_WORLD];   // every rank's control words: [0] arrivals (root's is used), [1] consumed
+    int world, root;
+};
+
+__device__ inline bool p2p_spin_ge(const volatile u64* p, u64 target) {
+    const long long t0 = clock64();
+    while (*p < target) {
+        if (clock64() - t0 > P2P_SPIN_CYCLES) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(const double* __restrict__ store, size_t n, double* __restrict__ root_inbox, u64* __restrict__ root_ctrl,
+                const u64* __restrict__ my_ctrl, u64 epoch, unsigned* __restrict__ done, double* __restrict__ err_flag) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = p2p_spin_ge(my_ctrl + 1, epoch - 1) ? 1 : 0;
+    __syncthreads();
+    if (ok) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            const double v = store[i];
+            if (v != 0.0) atomicAdd_system(root_inbox + i, v);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!ok) atomicAdd(err_flag, 1.0);
+        const unsigned d = atomicAdd(done, 1u);
+        if (d == gridDim.x - 1) {                    // last block of this rank: everything above is visible system-wide
+            *done = 0;
+            __threadfence_system();
+            atomicAdd_system(root_ctrl, 1ull);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+p2p_merge_kernel(double* __restrict__ store, double* __restrict__ inbox, size_t n, const u64* __restrict__ my_ctrl,
+                 u64 target_arrivals, u64 epoch, P2PPeers peers, int my_rank, unsigned* __restrict__ done,
+                 double* __restrict__ err_flag) {
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = p2p_spin_ge(my_ctrl, target_arrivals) ? 1 : 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = __ldcg(inbox + i);          // written by the peers' atomics in L2: bypass L1
+        if (v != 0.0) { store[i] += v; inbox[i] = 0.0; }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!ok) atomicAdd(err_flag, 1.0);
+        const unsigned d = atomicAdd(done, 1u);
+        if (d == gridDim.x - 1) {
+            *done = 0;
+            __threadfence_system();
+            for (int r = 0; r < peers.world; r++)
+                if (r != my_rank) atomicExch_system(peers.ctrl[r] + 1, epoch);
+        }
+    }
+}
+
+}  // namespace pipsort

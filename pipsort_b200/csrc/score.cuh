@@ -265,8 +265,9 @@ constexpr int SCORE_WARPS = 8;
 // Batch of union configurations in snp_map (user) order, -1 padded.
 __global__ void __launch_bounds__(SCORE_WARPS * 32)
 score_batch_kernel(LocusDev L, const int* __restrict__ idx, long long n, int kmax, int ws_kmax,
-                   const unsigned char* __restrict__ make_updates, double* __restrict__ out) {
+                   const unsigned char* __restrict__ make_updates, double* __restrict__ out, const int* __restrict__ n_extra) {
     extern __shared__ __align__(16) unsigned char smem[];
+    if (n_extra) n += *n_extra;          // batch length decided on the device (sss.cuh: 1 + number of unseen neighbours)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpWS ws = warp_ws(smem + (size_t)wib * warp_ws_bytes(ws_kmax), ws_kmax);
     const long long nw = (long long)gridDim.x * SCORE_WARPS;

@@ -42,10 +42,44 @@ def slice_bounds(n, world):
     return [(n * r) // world for r in range(world + 1)]
 
 
-def run_exhaustive_sharded(engine, c, group=None, bounds=None):
-    """reset + this rank's share of computeTotalLikelihood + ONE all-reduce(sum) of the accumulator store.
-    Asynchronous on the engine's stream; follow with engine.read() (every rank then holds the whole result)."""
+def connect_p2p(engine, group=None, root=0):
+    """Exchange the engines' mailbox handles (CUDA IPC) over the group and map every peer: after this the combine step
+    can run over NVLink peer memory (collective="p2p") instead of NCCL.  Returns False when IPC mapping is not possible
+    (the caller then stays with the all-reduce)."""
     world, rank = world_and_rank(group)
+    if world == 1:
+        return False
+    ok, mine = True, b""
+    try:
+        mine = engine.p2p_export()
+    except Exception:
+        ok = False
+    handles = [None] * world
+    _dist().all_gather_object(handles, mine if ok else b"", group=group)
+    if any(len(h) == 0 for h in handles):
+        return False
+    try:
+        engine.p2p_connect(handles, rank, root)
+    except Exception:
+        ok = False
+    flags = [None] * world
+    _dist().all_gather_object(flags, ok, group=group)
+    return all(flags)
+
+
+def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allreduce"):
+    """reset + this rank's share of computeTotalLikelihood + the combine step.  collective="allreduce": ONE all-reduce
+    (sum) of the accumulator store, every rank then holds the whole result.  collective="p2p" (after connect_p2p): the
+    non-root ranks add their stores into the root's memory over NVLink, only the root holds the result.
+    Asynchronous on the engine's stream; follow with engine.read()."""
+    world, rank = world_and_rank(group)
+    if collective == "p2p" and world > 1:
+        if bounds is None:
+            bounds = engine.shard_ranks(c, world)
+        engine.reset()
+        engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
+        engine.p2p_reduce_to_root()
+        return bounds
     if bounds is None:
         bounds = engine.shard_ranks(c, world)
     if len(bounds) != world + 1:
@@ -57,10 +91,15 @@ def run_exhaustive_sharded(engine, c, group=None, bounds=None):
     return bounds
 
 
-def compute_total_likelihood_sharded(engine, c=None, group=None, bounds=None):
-    """PostCal::computeTotalLikelihood (postcal.cpp:716) with the rank space sharded over the group."""
+def compute_total_likelihood_sharded(engine, c=None, group=None, bounds=None, collective="allreduce", root=0):
+    """PostCal::computeTotalLikelihood (postcal.cpp:716) with the rank space sharded over the group.  With
+    collective="p2p" only the root returns Results (the other ranks return None)."""
     c = engine.max_causal if c is None else c
-    run_exhaustive_sharded(engine, c, group, bounds)
+    run_exhaustive_sharded(engine, c, group, bounds, collective)
+    world, rank = world_and_rank(group)
+    if collective == "p2p" and world > 1 and rank != root:
+        engine.sync()
+        return None
     return engine.read()
 
 

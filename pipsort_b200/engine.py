@@ -20,6 +20,7 @@ _lib = None
 KEEP_ORDER = 1
 GENERIC_ONLY = 2
 RAW_LD = 4
+IPC_HANDLE_BYTES = 64
 KMAX = 8
 
 
@@ -69,15 +70,21 @@ def lib():
         L.pipsort_score_union_configs_device.argtypes = [vp, vp, C.c_int64, i32, vp, vp]
         L.pipsort_score_given_configs.argtypes = [vp, C.POINTER(C.c_int16), C.c_int64, i32]
         L.pipsort_score_given_configs_device.argtypes = [vp, vp, C.c_int64, i32]
+        L.pipsort_sss.argtypes = [vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.pipsort_sss_reset.argtypes = [vp]
         L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
         L.pipsort_finalize.argtypes = [vp]
         L.pipsort_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pipsort_config_count.argtypes = [vp, C.POINTER(u64)]
+        L.pipsort_last_read_config_count.argtypes = [vp, C.POINTER(u64)]
         L.pipsort_enumerate.argtypes = [vp, i32, u64, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                         C.POINTER(C.c_uint32)]
         L.pipsort_accumulator_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.pipsort_merge.argtypes = [vp, vp]
         L.pipsort_shard_ranks.argtypes = [vp, i32, i32, C.POINTER(u64)]
+        L.pipsort_p2p_export.argtypes = [vp, C.c_char_p]
+        L.pipsort_p2p_connect.argtypes = [vp, C.c_char_p, i32, i32, i32]
+        L.pipsort_p2p_reduce_to_root.argtypes = [vp]
         L.pipsort_shard_ranks_for_map.argtypes = [C.POINTER(C.c_int32), C.c_int32, i32, i32, C.c_uint32, C.POINTER(u64)]
         L.pipsort_stream.argtypes = [vp]
         L.pipsort_stream.restype = vp
@@ -238,6 +245,16 @@ class Engine:
         self.score_given_configs(configs)
         return self.read()
 
+    def sss(self, c=None, max_iterations=1000):
+        """sss_computeTotalLikelihood (sss_postcal.cpp:102-380): the whole stochastic shotgun search on a fresh set of
+        accumulators.  Returns (Results, iterations, stop_reason) with stop_reason 0 = iteration cap, 1 = no new
+        configuration ("hit break condition"), 2 = convergence."""
+        c = self.max_causal if c is None else c
+        it, why = C.c_int32(), C.c_int32()
+        self.reset()
+        _check(lib().pipsort_sss(self._h, int(c), int(max_iterations), C.byref(it), C.byref(why)))
+        return self.read(), int(it.value), int(why.value)
+
     def read(self) -> Results:
         total = np.zeros(1)
         post = np.zeros(self.N)
@@ -247,7 +264,9 @@ class Engine:
         nl = np.zeros(self.U)
         o = _Outputs(_dp(total), _dp(post), _dp(nc), _dp(sp), _dp(sl), _dp(nl))
         _check(lib().pipsort_read_accumulators(self._h, C.byref(o)))
-        return Results(float(total[0]), post, nc, sp, sl, nl, self.config_count())
+        cnt = C.c_uint64()
+        _check(lib().pipsort_last_read_config_count(self._h, C.byref(cnt)))
+        return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
 
     def finalize(self):
         _check(lib().pipsort_finalize(self._h))
@@ -281,6 +300,21 @@ class Engine:
 
     def merge_from(self, other: "Engine"):
         _check(lib().pipsort_merge(self._h, other._h))
+
+    def p2p_export(self) -> bytes:
+        """CUDA IPC handle of this engine's mailbox (64 bytes) for the peer-memory combine step."""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(lib().pipsort_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_connect(self, handles, rank, root=0):
+        """handles: list of every rank's p2p_export() bytes, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == IPC_HANDLE_BYTES * len(handles)
+        _check(lib().pipsort_p2p_connect(self._h, blob, len(handles), int(rank), int(root)))
+
+    def p2p_reduce_to_root(self):
+        _check(lib().pipsort_p2p_reduce_to_root(self._h))
 
     def shard_ranks(self, c, parts):
         b = (C.c_uint64 * (parts + 1))()

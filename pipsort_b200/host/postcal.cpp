@@ -101,7 +101,7 @@ void PostCal::read_results() {
     out.sharedLL = sharedLL.data();
     out.notSharedLL = notSharedLL.data();
     check(pipsort_read_accumulators(eng, &out));
-    check(pipsort_config_count(eng, &n_configs));
+    check(pipsort_last_read_config_count(eng, &n_configs));
 }
 
 // postcal.cpp:716-1092: every union subset of size <= maxCausalSNP, every expansion
@@ -212,6 +212,19 @@ double PostCal::sss_computeTotalLikelihood() {
         std::cout << "Error: at most " << PIPSORT_KMAX << " causal SNPs are supported" << std::endl;
         std::exit(1);
     }
+    const char* hl = std::getenv("PIPSORT_SSS_HOSTLOOP");
+    if (!(hl && *hl == '1')) {
+        // default: the whole search runs behind the C-ABI with the explored-configuration map in device memory
+        int32_t iters = 0, why = 0;
+        check(pipsort_sss(eng, maxCausalSNP, 1000, &iters, &why));       // total_iteration = 1000, sss_postcal.cpp:155
+        if (why == 1) printf("hit break condition\n");
+        if (why == 2) printf("hit convergence condition\n");
+        sss_iterations = iters;
+        read_results();
+        return totalLikeLihoodLOG;
+    }
+    // PIPSORT_SSS_HOSTLOOP=1: the same search with the neighbourhood lists and the map on the host (std::map), one
+    // batched scoring call per iteration -- kept as an independently written cross-check of pipsort_sss
     std::mt19937 gen(12345);                                             // sss_postcal.cpp:138
     std::vector<int> causal_locs;
     const int kmax = std::max(maxCausalSNP, 1);

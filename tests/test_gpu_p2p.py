@@ -1,0 +1,58 @@
+"""The peer-memory combine step (p2p.cuh: CUDA IPC mailboxes, system-scope fp64 atomics, device-side arrival / flow
+control words) with TWO processes.  Both ranks use cuda:0 when the box has a single GPU -- CUDA IPC maps another
+process's memory of the same device just as well, so export / connect / push / wait / merge / flow control all run for
+real; with two GPUs the ranks take one each and the atomics cross NVLink.  gloo only carries the 64-byte handles."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, assert_results_match, engine_for, oracle_locus
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, initfile, outdir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pipsort_b200 import distributed as D
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    try:
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        L = oracle_locus("small_example")
+        want = O.exhaustive(L, 3)
+        Le = oracle_locus("example", p=0.25)
+        with engine_for(L, 3, device=dev) as e, engine_for(Le, 2, device=dev) as e2:
+            assert D.connect_p2p(e)
+            assert D.connect_p2p(e2)
+            for rep in range(5):                       # several epochs: arrivals / consumed flow control
+                r = D.compute_total_likelihood_sharded(e, 3, collective="p2p")
+                if rank == 0:
+                    assert r.n_configs == want.n_eval == 268
+                    assert_results_match(r, want)
+                else:
+                    assert r is None
+            # lopsided caller-supplied split, and a locus whose log-likelihoods span thousands of nats (many bins)
+            r = D.compute_total_likelihood_sharded(e, 3, bounds=[0, 5, e.total_ranks(3)], collective="p2p")
+            if rank == 0:
+                assert_results_match(r, want)
+            r2 = D.compute_total_likelihood_sharded(e2, 2, collective="p2p")
+            if rank == 0:
+                from conftest import golden
+                assert r2.n_configs == 216817
+                assert_results_match(r2, golden("example_c2_p025"))
+        open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_combine_over_peer_memory():
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(2, os.path.join(tmp, "init"), tmp), nprocs=2, join=True)
+        assert os.path.exists(os.path.join(tmp, "ok0")) and os.path.exists(os.path.join(tmp, "ok1"))
