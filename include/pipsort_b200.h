@@ -220,6 +220,16 @@ void* pipsort_stream(pipsort_engine* e);
 int pipsort_set_stream(pipsort_engine* e, void* cuda_stream);
 int pipsort_sync(pipsort_engine* e);
 
+/* CUDA graphs.  Between pipsort_graph_begin and pipsort_graph_end the engine's asynchronous calls (pipsort_reset,
+ * pipsort_run_exhaustive, pipsort_score_*_device, pipsort_p2p_reduce_to_root, pipsort_finalize) are recorded instead of
+ * executed; pipsort_graph_launch replays the recorded sequence with ONE launch.  For a locus that takes 0.1 ms the host
+ * cost of issuing the half dozen launches of a pass is comparable to the pass itself; a driver that repeats the same
+ * pass (bootstrap / permutation replicates, benchmarks) replays the graph.  Run the sequence once normally first (the
+ * first pass allocates its scratch buffers), and do not call blocking entry points while capturing.              */
+int pipsort_graph_begin(pipsort_engine* e);
+int pipsort_graph_end(pipsort_engine* e, int32_t* graph_id);
+int pipsort_graph_launch(pipsort_engine* e, int32_t graph_id);
+
 /* Benchmark hygiene: evict L2 by overwriting a scratch buffer larger than L2 on the engine's stream. */
 int pipsort_flush_l2(pipsort_engine* e);
 

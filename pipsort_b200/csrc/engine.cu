@@ -192,6 +192,8 @@ struct pipsort_engine {
     int score_smem_set = 0;
     ExhScratch exh;
     bool use_reg_kernel = true;
+    bool capturing = false;
+    std::vector<cudaGraphExec_t> graphs;
     uint64_t last_read_count = 0;   // configuration count seen by the last pipsort_read_accumulators
     // stochastic shotgun search state (pipsort_sss): explored-configuration hash table + per-iteration buffers
     struct Sss {
@@ -330,6 +332,7 @@ void pipsort_destroy(pipsort_engine* e) {
         if (q.mailbox) cudaFree(q.mailbox);
         if (q.d_done) cudaFree(q.d_done);
     }
+    for (cudaGraphExec_t x : e->graphs) cudaGraphExecDestroy(x);
     if (e->d_idx) cudaFree(e->d_idx);
     if (e->d_upd) cudaFree(e->d_upd);
     if (e->d_out) cudaFree(e->d_out);
@@ -645,6 +648,39 @@ int pipsort_prep_info_get(const pipsort_engine* e, int study, pipsort_prep_info*
     return 0;
 }
 
+// ---- CUDA graphs: a fixed sequence of the engine's launches (reset + exhaustive + combine + finalize ...) replayed with
+// one call -- the launch-bound inner loop of a small locus ------------------------------------------------------------
+int pipsort_graph_begin(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (e->capturing) return fail(PIPSORT_E_ARG, "already capturing");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    e->capturing = true;
+    return 0;
+}
+
+int pipsort_graph_end(pipsort_engine* e, int32_t* graph_id) {
+    if (!e || !graph_id) return fail(PIPSORT_E_ARG, "null argument");
+    if (!e->capturing) return fail(PIPSORT_E_ARG, "not capturing");
+    e->capturing = false;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamEndCapture(e->stream, &g));
+    cudaGraphExec_t x = nullptr;
+    cudaError_t err = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) return fail(PIPSORT_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(err));
+    e->graphs.push_back(x);
+    *graph_id = (int32_t)e->graphs.size() - 1;
+    return 0;
+}
+
+int pipsort_graph_launch(pipsort_engine* e, int32_t graph_id) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    if (graph_id < 0 || (size_t)graph_id >= e->graphs.size()) return fail(PIPSORT_E_ARG, "unknown graph %d", graph_id);
+    CU(cudaGraphLaunch(e->graphs[graph_id], e->stream));
+    return 0;
+}
+
 int pipsort_reset(pipsort_engine* e) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
     CU(cudaSetDevice(e->device));
@@ -687,10 +723,10 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     // size classes 0..3: one launch of the register kernel (exhaustive.cuh); larger classes: generic kernel
     const int jreg = e->use_reg_kernel ? std::min(std::min(c, 3), e->U) : -1;
     if (jreg >= 0) {
-        if (jdom <= jreg) CU(cudaEventRecord(e->evk0, e->stream));
+        if (jdom <= jreg && !e->capturing) CU(cudaEventRecord(e->evk0, e->stream));
         if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh)))
             return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-        if (jdom <= jreg) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
+        if (jdom <= jreg && !e->capturing) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
     }
     u64 off = 0;
     for (int j = 0; j <= std::min(c, e->U); j++) {
@@ -699,7 +735,7 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
         if (lo < hi && j > jreg) {
             const u64 rb = lo - off, re = hi - off;
             const bool dominant = j == jdom;
-            if (dominant) CU(cudaEventRecord(e->evk0, e->stream));
+            if (dominant && !e->capturing) CU(cudaEventRecord(e->evk0, e->stream));
             size_t smem = 0;
             const int wk = std::max(j, 1);
             if ((rc = ensure_score_smem(e, wk, &smem))) return rc;
@@ -709,7 +745,7 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
             exhaustive_generic_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, j, rb, re, chunk, wk);
             e->launches++;
             CU(cudaGetLastError());
-            if (dominant) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
+            if (dominant && !e->capturing) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
         }
         off += cnt;
     }
@@ -1124,16 +1160,14 @@ int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
     if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
     if (q.world == 1) return 0;
     CU(cudaSetDevice(e->device));
-    q.epoch++;
     const size_t n = e->bins_len;
     const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)e->sm_count * 2);
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
     if (q.rank != q.root) {
         p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<double*>(q.peer_base[q.root]), q.peers.ctrl[q.root],
-                                                       q.peers.ctrl[q.rank], q.epoch, q.d_done, errf);
+                                                       q.peers.ctrl[q.rank], q.d_done, errf);
     } else {
-        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, q.peers.ctrl[q.rank],
-                                                        q.epoch * (u64)(q.world - 1), q.epoch, q.peers, q.rank, q.d_done, errf);
+        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
     }
     e->launches++;
     CU(cudaGetLastError());

@@ -22,7 +22,7 @@ constexpr int P2P_MAX_WORLD = 16;
 constexpr long long P2P_SPIN_CYCLES = 6000000000ll;   // ~3 s at 1.9 GHz
 
 struct P2PPeers {
-    u64* ctrl[P2P_MAX_WORLD];   // every rank's control words: [0] arrivals (root's is used), [1] consumed
+    u64* ctrl[P2P_MAX_WORLD];   // every rank's control words: [0] arrivals (root's is used), [1] consumed, [2] epoch (local)
     int world, root;
 };
 
@@ -37,9 +37,11 @@ __device__ inline bool p2p_spin_ge(const volatile u64* p, u64 target) {
 
 __global__ void __launch_bounds__(256)
 p2p_push_kernel(const double* __restrict__ store, size_t n, double* __restrict__ root_inbox, u64* __restrict__ root_ctrl,
-                const u64* __restrict__ my_ctrl, u64 epoch, unsigned* __restrict__ done, double* __restrict__ err_flag) {
+                u64* __restrict__ my_ctrl, unsigned* __restrict__ done, double* __restrict__ err_flag) {
     __shared__ int ok;
-    if (threadIdx.x == 0) ok = p2p_spin_ge(my_ctrl + 1, epoch - 1) ? 1 : 0;
+    // the epoch lives in device memory (control word 2, bumped by the last block) so that the launch has no per-step
+    // argument and can be replayed from a CUDA graph
+    if (threadIdx.x == 0) ok = p2p_spin_ge(my_ctrl + 1, *(volatile u64*)(my_ctrl + 2)) ? 1 : 0;   // consumed >= epoch - 1
     __syncthreads();
     if (ok) {
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -54,6 +56,7 @@ p2p_push_kernel(const double* __restrict__ store, size_t n, double* __restrict__
         const unsigned d = atomicAdd(done, 1u);
         if (d == gridDim.x - 1) {                    // last block of this rank: everything above is visible system-wide
             *done = 0;
+            my_ctrl[2] += 1;
             __threadfence_system();
             atomicAdd_system(root_ctrl, 1ull);
         }
@@ -61,12 +64,16 @@ p2p_push_kernel(const double* __restrict__ store, size_t n, double* __restrict__
 }
 
 __global__ void __launch_bounds__(256)
-p2p_merge_kernel(double* __restrict__ store, double* __restrict__ inbox, size_t n, const u64* __restrict__ my_ctrl,
-                 u64 target_arrivals, u64 epoch, P2PPeers peers, int my_rank, unsigned* __restrict__ done,
-                 double* __restrict__ err_flag) {
+p2p_merge_kernel(double* __restrict__ store, double* __restrict__ inbox, size_t n, u64* __restrict__ my_ctrl,
+                 P2PPeers peers, int my_rank, unsigned* __restrict__ done, double* __restrict__ err_flag) {
     __shared__ int ok;
-    if (threadIdx.x == 0) ok = p2p_spin_ge(my_ctrl, target_arrivals) ? 1 : 0;
+    __shared__ u64 epoch_s;
+    if (threadIdx.x == 0) {
+        epoch_s = *(volatile u64*)(my_ctrl + 2) + 1;
+        ok = p2p_spin_ge(my_ctrl, epoch_s * (u64)(peers.world - 1)) ? 1 : 0;    // every peer of this epoch has arrived
+    }
     __syncthreads();
+    const u64 epoch = epoch_s;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const double v = __ldcg(inbox + i);          // written by the peers' atomics in L2: bypass L1
         if (v != 0.0) { store[i] += v; inbox[i] = 0.0; }
@@ -78,6 +85,7 @@ p2p_merge_kernel(double* __restrict__ store, double* __restrict__ inbox, size_t 
         const unsigned d = atomicAdd(done, 1u);
         if (d == gridDim.x - 1) {
             *done = 0;
+            my_ctrl[2] = epoch;
             __threadfence_system();
             for (int r = 0; r < peers.world; r++)
                 if (r != my_rank) atomicExch_system(peers.ctrl[r] + 1, epoch);

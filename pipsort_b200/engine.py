@@ -82,6 +82,9 @@ def lib():
         L.pipsort_accumulator_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
         L.pipsort_merge.argtypes = [vp, vp]
         L.pipsort_shard_ranks.argtypes = [vp, i32, i32, C.POINTER(u64)]
+        L.pipsort_graph_begin.argtypes = [vp]
+        L.pipsort_graph_end.argtypes = [vp, C.POINTER(C.c_int32)]
+        L.pipsort_graph_launch.argtypes = [vp, C.c_int32]
         L.pipsort_p2p_export.argtypes = [vp, C.c_char_p]
         L.pipsort_p2p_connect.argtypes = [vp, C.c_char_p, i32, i32, i32]
         L.pipsort_p2p_reduce_to_root.argtypes = [vp]
@@ -300,6 +303,17 @@ class Engine:
 
     def merge_from(self, other: "Engine"):
         _check(lib().pipsort_merge(self._h, other._h))
+
+    def graph_begin(self):
+        _check(lib().pipsort_graph_begin(self._h))
+
+    def graph_end(self) -> int:
+        gid = C.c_int32()
+        _check(lib().pipsort_graph_end(self._h, C.byref(gid)))
+        return int(gid.value)
+
+    def graph_launch(self, graph_id):
+        _check(lib().pipsort_graph_launch(self._h, int(graph_id)))
 
     def p2p_export(self) -> bytes:
         """CUDA IPC handle of this engine's mailbox (64 bytes) for the peer-memory combine step."""

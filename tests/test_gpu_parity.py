@@ -245,3 +245,22 @@ def test_full_size_properties():
             r2 = e.read()
             assert r2.n_configs == r.n_configs
             assert_results_match(r2, r, rtol=1e-12)
+
+
+def test_graph_replay_reproduces_the_pass():
+    """reset + exhaustive + finalize recorded into a CUDA graph (pipsort_graph_begin/end) and replayed: identical results,
+    and the accumulators do not pile up across replays (the recorded reset is part of the graph)."""
+    from oracle import oracle as O
+    L = oracle_locus("small_example")
+    want = O.exhaustive(L, 3)
+    with engine_for(L, 3) as e:
+        first = e.compute_total_likelihood(3)          # allocates the scratch buffers outside the capture
+        e.graph_begin()
+        e.reset(); e.run_exhaustive(3); e.finalize()
+        gid = e.graph_end()
+        for _ in range(3):
+            e.graph_launch(gid)
+        r = e.read()
+    assert r.n_configs == first.n_configs == 268
+    assert_results_match(r, want)
+    assert r.total == pytest.approx(first.total, rel=1e-13)
