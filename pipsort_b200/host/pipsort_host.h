@@ -64,7 +64,8 @@ public:
 
 private:
     void read_results();
-    pipsort_engine* eng = nullptr;
+    pipsort_engine* eng = nullptr;                         // device 0 of the run: owns the merged accumulators
+    std::vector<pipsort_engine*> extra;                    // PIPSORT_DEVICES: one more engine per additional GPU
     int num_of_studies, totalSnpCount, unionSnpCount, maxCausalSNP;
     bool do_sss;
     std::vector<int> num_snps_all;

@@ -87,10 +87,30 @@ PostCal::PostCal(const std::vector<std::vector<double>>& sigma_eff, const std::v
     loc.gamma = gamma;
     loc.sharing_param = sharing_param;
     loc.max_causal = MAX_causal;
-    check(pipsort_create(&loc, device, 0, &eng));
+    // PIPSORT_DEVICES=0,1,...: one process drives several GPUs -- the locus is replicated, the rank space (or the rows of
+    // the explicit-configuration matrix) is split over the engines and the accumulator stores are added up (pipsort_merge)
+    std::vector<int> devices;
+    if (const char* dv = std::getenv("PIPSORT_DEVICES")) {
+        int v = 0;
+        bool have = false;
+        for (const char* q = dv;; q++) {
+            if (*q >= '0' && *q <= '9') { v = v * 10 + (*q - '0'); have = true; }
+            else { if (have) devices.push_back(v); v = 0; have = false; if (!*q) break; }
+        }
+    }
+    if (devices.empty()) devices.push_back(device);
+    check(pipsort_create(&loc, devices[0], 0, &eng));
+    for (size_t i = 1; i < devices.size(); i++) {
+        pipsort_engine* x = nullptr;
+        check(pipsort_create(&loc, devices[i], 0, &x));
+        extra.push_back(x);
+    }
 }
 
-PostCal::~PostCal() { pipsort_destroy(eng); }
+PostCal::~PostCal() {
+    for (pipsort_engine* x : extra) pipsort_destroy(x);
+    pipsort_destroy(eng);
+}
 
 void PostCal::read_results() {
     pipsort_outputs out;
@@ -114,7 +134,16 @@ double PostCal::computeTotalLikelihood() {
     }
     uint64_t total = 0;
     check(pipsort_total_ranks(eng, maxCausalSNP, &total));
-    check(pipsort_run_exhaustive(eng, maxCausalSNP, 0, total));
+    if (extra.empty()) {
+        check(pipsort_run_exhaustive(eng, maxCausalSNP, 0, total));
+    } else {
+        const int parts = 1 + (int)extra.size();
+        std::vector<uint64_t> b(parts + 1);
+        check(pipsort_shard_ranks(eng, maxCausalSNP, parts, b.data()));
+        check(pipsort_run_exhaustive(eng, maxCausalSNP, b[0], b[1]));                      // asynchronous: all devices run
+        for (int i = 1; i < parts; i++) check(pipsort_run_exhaustive(extra[i - 1], maxCausalSNP, b[i], b[i + 1]));
+        for (pipsort_engine* x : extra) check(pipsort_merge(eng, x));
+    }
     read_results();
     printf("num total configs = %llu\n", (unsigned long long)n_configs);
     return totalLikeLihoodLOG;
@@ -145,7 +174,15 @@ double PostCal::computeTotalLikelihoodGivenConfigs() {
         printf("config file is not the expected size\n");
         std::exit(1);
     }
-    check(pipsort_score_given_configs(eng, static_cast<const int16_t*>(map), num_configs, num_groups));
+    {
+        const int parts = 1 + (int)extra.size();
+        const int16_t* rows = static_cast<const int16_t*>(map);
+        for (int i = 0; i < parts; i++) {
+            const int64_t lo = (int64_t)num_configs * i / parts, hi = (int64_t)num_configs * (i + 1) / parts;
+            check(pipsort_score_given_configs(i == 0 ? eng : extra[i - 1], rows + lo * num_groups, hi - lo, num_groups));
+        }
+        for (pipsort_engine* x : extra) check(pipsort_merge(eng, x));
+    }
     if (len) munmap(map, len);
     read_results();
     printf("num total configs = %llu\n", (unsigned long long)n_configs);

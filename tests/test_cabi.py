@@ -63,6 +63,35 @@ def test_argument_errors_before_cuda():
     assert b"two studies" in lib.pipsort_last_error()
 
 
+def test_new_entry_points_reject_bad_arguments_without_touching_cuda():
+    import pipsort_b200 as P
+    lib = P.lib()
+    i32, u64 = ctypes.c_int32(), ctypes.c_uint64()
+    assert lib.pipsort_sss(None, 3, 1000, ctypes.byref(i32), ctypes.byref(i32)) == 1
+    assert lib.pipsort_sss_reset(None) == 1
+    assert lib.pipsort_score_given_configs(None, None, 0, 0) == 1
+    assert lib.pipsort_score_given_configs_device(None, None, 0, 0) == 1
+    assert lib.pipsort_p2p_export(None, None) == 1
+    assert lib.pipsort_p2p_connect(None, None, 2, 0, 0) == 1
+    assert lib.pipsort_p2p_reduce_to_root(None) == 1
+    assert lib.pipsort_graph_begin(None) == 1
+    assert lib.pipsort_graph_end(None, ctypes.byref(i32)) == 1
+    assert lib.pipsort_graph_launch(None, 0) == 1
+    assert lib.pipsort_prep_info_get(None, 0, None) == 1
+    assert lib.pipsort_last_read_config_count(None, ctypes.byref(u64)) == 1
+    assert lib.pipsort_preprocess_study(0, -1, None, None, None, None) == 1
+    smap = np.zeros((2, 4), dtype=np.int32)
+    b = (ctypes.c_uint64 * 3)()
+    assert lib.pipsort_shard_ranks_for_map(smap.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 4, 2, 0, 0, b) == 1
+    assert lib.pipsort_shard_ranks_for_map(smap.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 4, -1, 2, 0, b) == 1
+    assert P.shard_ranks_for_map(smap, 2, 2) == [0, P.shard_ranks_for_map(smap, 2, 2)[1], 11]     # 1 + 4 + 6 ranks
+    if not have_gpu():
+        ld = np.eye(3)
+        with pytest.raises(P.PipsortError) as ei:
+            P.preprocess_study(ld, np.zeros(3))
+        assert ei.value.code == 2 and "no CPU path" in str(ei.value)
+
+
 def test_synth_counts():
     from pipsort_b200 import synth
     L = synth.make_locus(150)

@@ -76,3 +76,22 @@ def test_cli_flag_quirks():
     assert p.returncode == 1 and "config file is not the expected size" in p.stdout
     p = subprocess.run(base + ["-d", "0", "-e", "5"], cwd=d, capture_output=True, text=True)
     assert p.returncode == 1 and "Number of configs must be greater than 0" in p.stdout
+
+
+def test_cli_several_devices_one_process():
+    """PIPSORT_DEVICES=0,1 (or 0,0 on a single-GPU box: two engines on one device exercise the same shard + merge path):
+    the rank space / the explicit-configuration rows are split over the engines, the stores merged -- same six files."""
+    import torch
+    devs = "0,1" if torch.cuda.device_count() > 1 else "0,0"
+    for name in ["example_c2_p025", "small_c3_p075", "example_given_mixed"]:
+        g = golden(name)
+        d = os.path.join(GOLDEN, g["dataset"])
+        with tempfile.TemporaryDirectory() as tmp:
+            out = os.path.join(tmp, "o")
+            cmd = [host_bin(), "-l", "ldfiles.txt", "-z", "zfiles.txt", "-m", MAPS[g["dataset"]], "-n", g["sample_sizes"],
+                   "-o", out] + [os.path.join(GOLDEN, a[1:]) if a.startswith("@") else a for a in g["args"]]
+            p = subprocess.run(cmd, cwd=d, capture_output=True, text=True, env=dict(os.environ, PIPSORT_DEVICES=devs))
+            assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+            for suf, want in g["files"].items():
+                with open(f"{out}_{suf}.txt") as f:
+                    assert f.read() == want, f"{name}: {suf} differs"

@@ -264,3 +264,40 @@ def test_graph_replay_reproduces_the_pass():
     assert r.n_configs == first.n_configs == 268
     assert_results_match(r, want)
     assert r.total == pytest.approx(first.total, rel=1e-13)
+
+
+@pytest.mark.parametrize("p", [0.25, 0.75])
+def test_baseline_config_a_300_snps_c2(p):
+    """BASELINE.json configs[2] at full size: synthetic 300-SNP/study locus, 80 % overlap (U = 360), c = 2 exhaustive
+    (352,501 configurations), p = 0.25 and 0.75 -- every accumulator against the oracle, as one run and as the 1 / 2 / 4 / 8
+    rank-range shards the multi-GPU path hands out (accumulated on one engine: the stores are additive)."""
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    SL = synth.make_locus(300, overlap=0.8, sharing_param=p)
+    assert SL.U == 360 and synth.count_configs(SL.snp_map, 2) == 352501
+    want = O.exhaustive(synth_as_oracle_locus(SL), 2)
+    with engine_for(SL, 2) as e:
+        r = e.compute_total_likelihood(2)
+        assert r.n_configs == want.n_eval == 352501
+        assert_results_match(r, want)
+        for parts in (2, 4, 8):
+            b = e.shard_ranks(2, parts)
+            e.reset()
+            for i in range(parts):
+                e.run_exhaustive(2, b[i], b[i + 1])
+            rs = e.read()
+            assert rs.n_configs == 352501
+            assert_results_match(rs, want)
+
+
+def test_baseline_config_b_150_snps_c3_sampled_against_oracle():
+    """BASELINE.json configs[3] (150 SNPs/study, c = 3, 12,197,751 configurations): the oracle needs a few seconds for the
+    whole run, so compare everything."""
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    SL = synth.make_locus(150, overlap=0.8)
+    want_total, want_n = O.exhaustive_omp(synth_as_oracle_locus(SL), 3, 0, O.total_union_subsets(SL.U, 3), 0)
+    with engine_for(SL, 3) as e:
+        r = e.compute_total_likelihood(3)
+    assert r.n_configs == want_n == 12197751
+    assert r.total == pytest.approx(want_total, rel=1e-10)
