@@ -722,6 +722,25 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     }
     // size classes 0..3: one launch of the register kernel (exhaustive.cuh); larger classes: generic kernel
     const int jreg = e->use_reg_kernel ? std::min(std::min(c, 3), e->U) : -1;
+    if (jreg >= 2 && !e->L.st[0].P) {
+        // first exhaustive run with pairs / triples: build the pair tables E_s{i,j} (n_s^2 doubles per study, once)
+        if (e->capturing) return fail(PIPSORT_E_ARG, "run the pass once before capturing it (the first run builds the pair tables)");
+        for (int s = 0; s < 2; s++) {
+            StudyDev& st = e->L.st[s];
+            double* P = nullptr;
+            CU(cudaMallocAsync(&P, (size_t)std::max(st.n, 1) * std::max(st.ldw, 1) * sizeof(double), e->stream));
+            e->allocs.push_back(P);
+            if (st.n > 0) {
+                dim3 grid((st.ldw + 127) / 128, st.n);
+                pair_table_kernel<<<grid, 128, 0, e->stream>>>(st, P);
+                e->launches++;
+            }
+            st.P = P;
+        }
+        CU(cudaGetLastError());
+        e->L_host_copy = e->L;
+        CU(cudaMemcpyAsync(e->d_L, &e->L_host_copy, sizeof(LocusDev), cudaMemcpyHostToDevice, e->stream));
+    }
     if (jreg >= 0) {
         if (jdom <= jreg && !e->capturing) CU(cudaEventRecord(e->evk0, e->stream));
         if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh)))
@@ -1203,16 +1222,42 @@ static int shard_by_types(const std::vector<int>& types, int c, int parts, uint6
         }
     }
     WorkModel wm(types, std::max(cc, 1));
+    // Cost model.  Size classes 2 and 3 run in the register kernel, whose unit of work is a WARP-STEP (a, b, 32-wide
+    // tile of x): its cost hardly depends on how many of the 27 expansions exist (absent ones are multiplications by
+    // zero), only on whether the bordered Cholesky steps of a study can be skipped for the whole tile.  So a segment of
+    // ranks is weighted by its warp-steps (0.5 + 0.25 per study that has both b and some x of the tile), not by its
+    // expanded configurations -- the study-specific SNPs at the end of the internal order have 27x fewer
+    // configurations per subset but cost nearly the same.  Larger classes (generic kernel, one warp per subset)
+    // are weighted per subset.
+    const int ntile = U > 0 ? ((U - 1) >> 5) + 1 : 0;
+    std::vector<double> sp(ntile + 1, 0.0), s0(ntile + 1, 0.0), s1(ntile + 1, 0.0);   // suffix sums over tiles
+    for (int t = ntile - 1; t >= 0; t--) {
+        bool h0 = false, h1 = false;
+        for (int x = t * 32; x < std::min(U, t * 32 + 32); x++) { h0 |= types[x] == 0 || types[x] == 1; h1 |= types[x] == 0 || types[x] == 2; }
+        sp[t] = sp[t + 1] + 1.0; s0[t] = s0[t + 1] + (h0 ? 1.0 : 0.0); s1[t] = s1[t + 1] + (h1 ? 1.0 : 0.0);
+    }
+    auto tcost = [&](int b) -> double {          // warp-steps of (., b, all tiles of x > b)
+        if (b + 1 >= U) return 0.0;
+        const int t0 = (b + 1) >> 5;
+        const bool in0 = types[b] == 0 || types[b] == 1, in1 = types[b] == 0 || types[b] == 2;
+        return 0.5 * sp[t0] + (in0 ? 0.25 * s0[t0] : 0.0) + (in1 ? 0.25 * s1[t0] : 0.0);
+    };
+    std::vector<double> w3(U + 1, 0.0);           // w3[a] = sum over b > a
+    for (int a = U - 2; a >= 0; a--) w3[a] = w3[a + 1] + tcost(a + 1);
     // segments of consecutive ranks (size class j, smallest element g) with their work estimate
     struct Seg { u64 begin, count; double work; };
     std::vector<Seg> segs;
     u64 off = 0;
-    const double per_subset = 8.0;   // Cholesky work is per union subset, the rest per expanded configuration
     for (int j = 0; j <= cc; j++) {
-        if (j == 0) { segs.push_back({off, 1, 1.0}); off += 1; continue; }
+        if (j == 0) { segs.push_back({off, 1, 0.01}); off += 1; continue; }
         for (int g = 0; g + j <= U; g++) {
             const u64 cnt = binom_host(U - 1 - g, j - 1, nullptr);
-            segs.push_back({off, cnt, wm.configs_first(j, g) + per_subset * (double)cnt});
+            double work;
+            if (j == 1) work = 1.0 / 32.0;
+            else if (j == 2) work = 0.8 * tcost(g);
+            else if (j == 3) work = w3[g];
+            else work = (0.3 * wm.configs_first(j, g) / std::max(1.0, wm.w[g]) + 3.0 * (double)cnt);   // generic kernel: per subset
+            segs.push_back({off, cnt, work});
             off += cnt;
         }
     }

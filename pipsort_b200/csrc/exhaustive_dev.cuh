@@ -85,6 +85,32 @@ __device__ __forceinline__ double extend_fast(double base, double hd, double r, 
     return base * (exp_pos(hd * (u * u)) * rs);
 }
 
+// Pair table of one study: P[i][j] = E{i,j} = E{i} * exp(hd r^2 / s) / sqrt(s),  s = A_j - W_ij^2 / A_i,  r = z_j - W_ij z_i / A_i.
+// E{b,x} does not depend on the third SNP of a triple, so the exhaustive kernel would otherwise recompute each entry once
+// per `a` (U times): n^2 exponentials here replace n^3/3 there.  Values outside the fast range (or a lost positive
+// definiteness) are stored as +inf: the kernel then sends the subset down its mantissa/exponent path, which also
+// raises the error flag where the reference would stop.
+__global__ void __launch_bounds__(128) pair_table_kernel(StudyDev S, double* __restrict__ P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= S.ldw || i >= S.n) return;
+    double v = 0.0;
+    if (j < S.n && j != i) {
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        const int n = S.e1n[i];
+        const double W = S.W[(size_t)i * S.ldw + j];
+        const double s = fma(-W * W, S.invA[i], S.A[j]);
+        const double r = fma(-W, S.u[i], S.z[j]);
+        v = inf;
+        if (n < 440 && s > 0.25) {
+            int bad = 0;
+            v = extend_fast(scale2(S.e1m[i], n), S.hd, r, s, bad);
+            if (!(v < FAST_LIMIT)) v = inf;
+        }
+    }
+    P[(size_t)i * S.ldw + j] = v;
+}
+
 constexpr __host__ __device__ bool in0(int t) { return t != 1; }   // state 0: study 0 only, 1: study 1 only, 2: both
 constexpr __host__ __device__ bool in1(int t) { return t != 0; }
 
@@ -214,8 +240,6 @@ struct WinStudy {
     double Wab[EXH_BW];    // d Sigma[a][b]                      (0 when a or b is absent from the study)
     double inv22[EXH_BW];  // 1 / Schur(b | a)
     double c2[EXH_BW];     // residual(b | a) / Schur(b | a)
-    double invAb[EXH_BW];  // 1 / A_b
-    double ub[EXH_BW];     // z_b / A_b
     double v2[EXH_BW];     // E{b}   (0 when b is absent from the study)
     double v3[EXH_BW];     // E{a,b} (0 when a or b is absent)
     int locb[EXH_BW];      // study-local index of b or -1
@@ -292,9 +316,9 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 WinStudy& w = win.st[s];
                 const int lb = bv ? L.loc[s][b] : -1;
                 const bool hb = lb >= 0;
-                double Wab = 0.0, invAb = 1.0, ub = 0.0, Ab = 1.0, zb = 0.0, v2 = 0.0, v3 = 0.0;
+                double Wab = 0.0, Ab = 1.0, zb = 0.0, v2 = 0.0, v3 = 0.0;
                 if (hb) {
-                    invAb = S.invA[lb]; ub = S.u[lb]; Ab = S.A[lb]; zb = S.z[lb];
+                    Ab = S.A[lb]; zb = S.z[lb];
                     const int n = S.e1n[lb];
                     okb &= n < 440;
                     v2 = scale2(S.e1m[lb], min(n, 900));
@@ -305,11 +329,11 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 const double r2 = fma(-Wab, ua[s], zb);
                 const double inv22 = 1.0 / s22;
                 if (HAS_A && ha[s] && hb) {
-                    v3 = extend_fast(v1[s], S.hd, r2, s22, bad);
+                    bad |= !(s22 > 0.25);
+                    v3 = S.P[(size_t)la[s] * S.ldw + lb];                // E{a,b} from the pair table
                     okb &= v3 < FAST_LIMIT;
                 }
                 w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = r2 * inv22;
-                w.invAb[lane] = invAb; w.ub[lane] = ub;
                 w.v2[lane] = v2; w.v3[lane] = v3;
                 w.locb[lane] = lb;
             }
@@ -349,7 +373,8 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 cx[s] = fma(-Wax, px[s], Ax[s]);
                 rx[s] = fma(-Wax, ua[s], zx[s]);
                 if (HAS_A && ha[s] && hx[s]) {
-                    v5[s] = extend_fast(v1[s], S.hd, rx[s], cx[s], bad);
+                    bad |= !(cx[s] > 0.25);
+                    v5[s] = S.P[(size_t)la[s] * S.ldw + lx[s]];          // E{a,x}
                     okX = okX && v5[s] < FAST_LIMIT;
                 }
             }
@@ -358,11 +383,14 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             const int nstates_x = hx[0] && hx[1] ? 3 : (hx[0] || hx[1] ? 1 : 0);
             double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             const bool diag = P.partial || (b0 + nb - 1 >= xt * 32);     // some lane may be inactive at some step
-            double wnext[2];                                             // W[b][x] of the NEXT step (software prefetch)
+            double wnext[2], pnext[2];                                   // W[b][x], E{b,x} of the NEXT step (software prefetch)
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const int lb = win.st[s].locb[0];
-                wnext[s] = (lb >= 0 && hx[s]) ? L.st[s].W[(size_t)lb * L.st[s].ldw + lx[s]] : 0.0;
+                const bool h = lb >= 0 && hx[s];
+                const size_t o = h ? (size_t)lb * L.st[s].ldw + lx[s] : 0;
+                wnext[s] = h ? L.st[s].W[o] : 0.0;
+                pnext[s] = h ? L.st[s].P[o] : 0.0;
             }
 
             // b cells of the PREVIOUS step: their warp reduction is issued at the top of the next step so that its
@@ -403,17 +431,21 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     double e6 = 0.0, e7 = 0.0;
 #if EXH_PREFETCH
                     const double Wbx = wnext[s];
+                    const double Pbx = pnext[s];
                     if (t + 1 < nb) {
                         const int lbn = w.locb[t + 1];
-                        wnext[s] = (lbn >= 0 && hx[s]) ? S.W[(size_t)lbn * S.ldw + lx[s]] : 0.0;
+                        const bool h = lbn >= 0 && hx[s];
+                        const size_t o = h ? (size_t)lbn * S.ldw + lx[s] : 0;
+                        wnext[s] = h ? S.W[o] : 0.0;
+                        pnext[s] = h ? S.P[o] : 0.0;
                     }
 #else
-                    const double Wbx = (hb[s] && hx[s]) ? S.W[(size_t)lb * S.ldw + lx[s]] : 0.0;
+                    const size_t o = (hb[s] && hx[s]) ? (size_t)lb * S.ldw + lx[s] : 0;
+                    const double Wbx = (hb[s] && hx[s]) ? S.W[o] : 0.0;
+                    const double Pbx = (hb[s] && hx[s]) ? S.P[o] : 0.0;
 #endif
                     if (hb[s] && hx[s]) {
-                        const double s6 = fma(-Wbx * Wbx, w.invAb[t], Ax[s]);
-                        const double r6 = fma(-Wbx, w.ub[t], zx[s]);
-                        e6 = extend_fast(w.v2[t], S.hd, r6, s6, bad);
+                        e6 = Pbx;                                        // E{b,x} from the pair table
                         if (HAS_A && ha[s]) {
                             const double tt = fma(-w.Wab[t], px[s], Wbx);
                             const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
@@ -600,15 +632,13 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 for (int k = HAS_A ? 0 : 5; k < 8; k++) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
                 cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
             }
-            if (lane == 0) {
-                if (HAS_A) {
+            {   // every lane holds all eight sums after the butterfly: lane k flushes sum k (one bin_add deep, not eight)
+                double mine = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 5; k++) bin_add(acc, k, a, r[k], 0);
-                }
-                bin_add(acc, SCAL, S_TOTAL, r[5], 0);
-                bin_add(acc, SCAL, S_NC0, r[6], 0);
-                bin_add(acc, SCAL, S_NC1, r[7], 0);
-                count_add(acc, (u64)cnt);
+                for (int k = 0; k < 8; k++) if (lane == k) mine = r[k];
+                if (lane < 5) { if (HAS_A) bin_add(acc, lane, a, mine, 0); }
+                else if (lane < 8) bin_add(acc, SCAL, lane == 5 ? S_TOTAL : (lane == 6 ? S_NC0 : S_NC1), mine, 0);
+                if (lane == 0) count_add(acc, (u64)cnt);
             }
             if (__any_sync(0xffffffffu, bad) && lane == 0) flag_set(acc, ERR_NOT_PD);
         }
