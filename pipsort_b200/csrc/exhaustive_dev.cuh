@@ -78,9 +78,19 @@ __device__ __forceinline__ E2 extend(const E2& base, double hd, double r, double
     xexp(hd * (u * u), em, en);
     return E2{base.m * (em * rs), base.n + en};
 }
+// 1/sqrt(s) for s of ordinary magnitude (here: Schur complements >= 1 up to rounding): the MUFU.RSQ64H seed (2^-22)
+// followed by one third-order correction  y0 (1 + e/2 + 3 e^2/8),  e = 1 - s y0^2  (error 5 e^3/16 < 2^-66).  The library
+// rsqrt() wraps the same sequence in a branch + call for denormal / infinite arguments; that branch ends the basic block
+// and keeps the compiler from interleaving the two studies' dependency chains.
+__device__ __forceinline__ double rsqrt_fast(double s) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s));
+    const double e = fma(s, -(y0 * y0), 1.0);
+    return fma(fma(e, 0.375, 0.5), y0 * e, y0);
+}
 __device__ __forceinline__ double extend_fast(double base, double hd, double r, double s, int& bad) {
     bad |= !(s > 0.25);
-    const double rs = rsqrt(s);
+    const double rs = rsqrt_fast(s);
     const double u = r * rs;
     return base * (exp_pos(hd * (u * u)) * rs);
 }
@@ -422,36 +432,30 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 double v[2][8];
                 int hb[2];
                 bool ok = okX && win.ok[t];
+                // Branch-free on purpose: both studies' chains (bordered Cholesky step -> rsqrt -> exp) sit in ONE basic
+                // block so that the compiler interleaves them.  Absent SNPs are "virtual" (W = 0, A = 1, z = 0, E = 0): the
+                // arithmetic stays finite and the zero base E{a,b} or the final select switch the expansion off.
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     const StudyDev& S = L.st[s];
                     const WinStudy& w = win.st[s];
-                    const int lb = w.locb[t];
-                    hb[s] = lb >= 0;
-                    double e6 = 0.0, e7 = 0.0;
-#if EXH_PREFETCH
+                    hb[s] = w.locb[t] >= 0;
                     const double Wbx = wnext[s];
-                    const double Pbx = pnext[s];
-                    if (t + 1 < nb) {
-                        const int lbn = w.locb[t + 1];
+                    const double e6 = pnext[s];                          // E{b,x} from the pair table (0 when b or x is absent)
+                    {
+                        const int lbn = w.locb[min(t + 1, nb - 1)];     // next step's W[b][x], E{b,x} (software prefetch)
                         const bool h = lbn >= 0 && hx[s];
                         const size_t o = h ? (size_t)lbn * S.ldw + lx[s] : 0;
                         wnext[s] = h ? S.W[o] : 0.0;
                         pnext[s] = h ? S.P[o] : 0.0;
                     }
-#else
-                    const size_t o = (hb[s] && hx[s]) ? (size_t)lb * S.ldw + lx[s] : 0;
-                    const double Wbx = (hb[s] && hx[s]) ? S.W[o] : 0.0;
-                    const double Pbx = (hb[s] && hx[s]) ? S.P[o] : 0.0;
-#endif
-                    if (hb[s] && hx[s]) {
-                        e6 = Pbx;                                        // E{b,x} from the pair table
-                        if (HAS_A && ha[s]) {
-                            const double tt = fma(-w.Wab[t], px[s], Wbx);
-                            const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
-                            const double r7 = fma(-tt, w.c2[t], rx[s]);
-                            e7 = extend_fast(w.v3[t], S.hd, r7, s7, bad);
-                        }
+                    double e7 = 0.0;
+                    if (HAS_A) {
+                        const double tt = fma(-w.Wab[t], px[s], Wbx);
+                        const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
+                        const double r7 = fma(-tt, w.c2[t], rx[s]);
+                        const double e = extend_fast(w.v3[t], S.hd, r7, s7, bad);   // v3 = 0 when a or b is absent
+                        e7 = hx[s] ? e : 0.0;
                     }
                     ok = ok && (e6 < FAST_LIMIT) && (e7 < FAST_LIMIT);
                     v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
@@ -460,9 +464,13 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 const int nstates_b = hb[0] && hb[1] ? 3 : (hb[0] || hb[1] ? 1 : 0);
                 if (active) nconf += (unsigned)(nstates_a * nstates_b * nstates_x);
                 if (active && !ok) slow_subset<J>(*Lg, a, b, x);      // rare, divergent, self-contained
-                if (!(active && ok)) {                              // this lane contributes nothing on the fast path
+                {                                                   // a lane that is off contributes nothing on the fast path
+                    const bool on = active && ok;
 #pragma unroll
-                    for (int s = 0; s < 2; s++) { v[s][4] = 0.0; v[s][5] = 0.0; v[s][6] = 0.0; v[s][7] = 0.0; }
+                    for (int s = 0; s < 2; s++) {
+                        v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
+                        v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
+                    }
                 }
 
                 // ---- cells: g[state][a'] = sum over the expansions with one SNP in that state, a' = number of
