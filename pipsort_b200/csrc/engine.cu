@@ -742,10 +742,11 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
         CU(cudaMemcpyAsync(e->d_L, &e->L_host_copy, sizeof(LocusDev), cudaMemcpyHostToDevice, e->stream));
     }
     if (jreg >= 0) {
-        if (jdom <= jreg && !e->capturing) CU(cudaEventRecord(e->evk0, e->stream));
-        if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh)))
+        const bool timed = jdom <= jreg && !e->capturing;
+        if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh,
+                                        timed ? e->evk0 : nullptr, timed ? e->evk1 : nullptr)))
             return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-        if (jdom <= jreg && !e->capturing) { CU(cudaEventRecord(e->evk1, e->stream)); e->evk_valid = true; }
+        if (timed) e->evk_valid = true;
     }
     u64 off = 0;
     for (int j = 0; j <= std::min(c, e->U); j++) {

@@ -1,6 +1,7 @@
 // Exhaustive path: device code in exhaustive_dev.cuh, host-side work decomposition + launch below.
 #pragma once
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -19,6 +20,11 @@ struct ExhScratch {           // owned by the engine, reused across launches
     int occ = 0;              // resident blocks per SM of exhaustive_all_kernel
     // key of the prefix table currently on the device
     int k_U = -1, k_bw = 0, k_xch = 0, k_alo = 0, k_ahi = 0;
+    // the work decomposition of the last launch (a pass is usually repeated with the same c and rank range)
+    bool plan_valid = false;
+    int plan_c = 0;
+    unsigned long long plan_rb = 0, plan_re = 0;
+    unsigned char plan[512];
 };
 
 inline u64 exh_binom(int n, int k) {
@@ -78,15 +84,31 @@ inline bool exh_class_params(ExhParams& P, int U, int j, u64 rb, u64 re) {
 
 // Launches ONE kernel for the size classes 0..min(c,3) restricted to the global union-subset rank range
 // [rank_begin, rank_end) (size-then-lexicographic order over the internal SNP order).  Returns a cudaError_t.
+// ev0 / ev1 (optional) are recorded immediately around the kernel launch: the host-side planning below and the reset of
+// the work-queue head are NOT part of the kernel's device time.
 inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u64 rank_begin, u64 rank_end, int sm_count,
-                                 cudaStream_t stream, unsigned long long* launches, ExhScratch* sc) {
+                                 cudaStream_t stream, unsigned long long* launches, ExhScratch* sc, cudaEvent_t ev0 = nullptr,
+                                 cudaEvent_t ev1 = nullptr) {
     const int U = L.U;
     cudaError_t err;
+    static_assert(sizeof(ExhAll) <= sizeof(sc->plan), "plan cache too small");
     if (!sc->d_counter) {
         if ((err = cudaMallocAsync(&sc->d_counter, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
         if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
     }
     ExhAll A;
+    const bool knobs = getenv("PIPSORT_EXH_BW") || getenv("PIPSORT_EXH_ITEMS_PER_SLOT");   // experiments: plan afresh
+    if (sc->plan_valid && !knobs && sc->plan_c == c && sc->plan_rb == rank_begin && sc->plan_re == rank_end) {
+        memcpy(&A, sc->plan, sizeof A);
+        if (A.n_total == 0) return 0;
+        if ((err = cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
+        const int blocks = (int)std::min<u64>((A.n_total + EXH_WARPS - 1) / EXH_WARPS, (u64)sm_count * std::max(1, sc->occ));
+        if (ev0 && (err = cudaEventRecord(ev0, stream)) != cudaSuccess) return (int)err;
+        exhaustive_all_kernel<<<blocks, EXH_WARPS * 32, 0, stream>>>(L, A, Lg);
+        if (ev1 && (err = cudaEventRecord(ev1, stream)) != cudaSuccess) return (int)err;
+        (*launches)++;
+        return (int)cudaGetLastError();
+    }
     memset(&A, 0, sizeof A);
     u64 off = 0;
     bool have3 = false, have2 = false;
@@ -104,23 +126,40 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     }
     const int occ = std::max(1, sc->occ);
     const u64 slots = (u64)sm_count * occ * EXH_WARPS;
-    static const int per_slot = [] {   // items per resident warp (tuning knob, default 6)
+    // Granularity (measured on B200, scripts/sweep_bw.sh): the full 32-wide b-window amortises the window table and the
+    // per-tile x values best at every locus size; the number of x tiles per item is the largest one that still leaves
+    // about a dozen items per resident warp for the work queue to balance (150 SNPs/study: (32,1), 0.068 ms instead of
+    // 0.079 with 16-wide windows; 300: (32,1), 0.29 instead of 0.48 ms; 600: (32,3)).  Only loci with fewer items than
+    // resident warps fall back to narrower windows.
+    const int per_slot = [] {   // items per resident warp to aim for (tuning knob; read per launch so one process can sweep it)
         const char* v = getenv("PIPSORT_EXH_ITEMS_PER_SLOT");
         const int k = v ? atoi(v) : 0;
-        return k > 0 ? k : 6;
+        return k > 0 ? k : 12;
     }();
-    // granularity: large items amortise the per-item setup, but there must be enough of them to balance
-    const int cand[][2] = {{32, 1 << 20}, {32, 16}, {32, 8}, {32, 4}, {32, 2}, {32, 1}, {16, 1}, {8, 1}};
+    const int force_bw = [] { const char* v = getenv("PIPSORT_EXH_BW"); return v ? atoi(v) : 0; }();   // experiments
+    const int force_xch = [] { const char* v = getenv("PIPSORT_EXH_XCH"); return v && atoi(v) > 0 ? atoi(v) : 1; }();
+    auto choose = [&](auto count_items, u64 already, int& bw, int& xch) -> u64 {
+        if (force_bw > 0) { bw = force_bw; xch = force_xch; return count_items(bw, xch); }
+        const int xchs[] = {1 << 20, 32, 16, 12, 8, 6, 4, 3, 2, 1};
+        u64 n = 0;
+        bw = 32;
+        for (int x : xchs) {
+            xch = x;
+            n = count_items(bw, xch);
+            if (n + already >= (u64)per_slot * slots) return n;
+        }
+        for (int w : {32, 16, 8}) {   // small locus: narrower windows only when full ones leave most warps without any item
+            bw = w; xch = 1;          // (150 SNPs/study: 1678 items of (32,1) on 1776 warps beat 3020 items of (16,1))
+            n = count_items(bw, xch);
+            if ((n + already) * 10 >= slots * 9) break;
+        }
+        return n;
+    };
     std::vector<u64> prefix;
     if (have3) {
         ExhParams& P = A.p3;
-        for (const auto& cd : cand) {
-            P.bw = cd[0]; P.xch = cd[1];
-            u64 n = 0;
-            for (int a = P.a_lo; a <= P.a_hi; a++) n += exh_items_of(U, a, P.bw, P.xch);
-            A.n3 = n;
-            if (n >= (u64)per_slot * slots) break;
-        }
+        A.n3 = choose([&](int bw, int xch) { u64 n = 0; for (int a = P.a_lo; a <= P.a_hi; a++) n += exh_items_of(U, a, bw, xch); return n; },
+                      0, P.bw, P.xch);
         if (A.n3 >= 0xfff00000ull) return (int)cudaErrorInvalidValue;   // 32-bit work queue (never in practice)
         if (!(sc->k_U == U && sc->k_bw == P.bw && sc->k_xch == P.xch && sc->k_alo == P.a_lo && sc->k_ahi == P.a_hi)) {
             prefix.push_back(0);
@@ -138,19 +177,30 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     }
     if (have2) {
         ExhParams& P = A.p2;
-        for (const auto& cd : cand) {
-            P.bw = cd[0]; P.xch = cd[1];
-            A.n2 = exh_items_of(U, -1, P.bw, P.xch);
-            if (A.n2 + A.n3 >= (u64)per_slot * slots || (have3 && A.n2 >= slots / 4)) break;
-        }
+        if (have3) { P.bw = 32; P.xch = 1; A.n2 = exh_items_of(U, -1, P.bw, P.xch); }   // a sliver next to the triples: finest items
+        else A.n2 = choose([&](int bw, int xch) { return exh_items_of(U, -1, bw, xch); }, 0, P.bw, P.xch);
         P.n_items = A.n2;
     }
     A.n_total = A.n3 + A.n2 + (u64)A.n1_tiles + (u64)A.do_null;
     if (A.n_total == 0) return 0;
+    static const bool debug = getenv("PIPSORT_EXH_DEBUG") != nullptr;
+    if (debug) {
+        const unsigned char* q = reinterpret_cast<const unsigned char*>(&A);
+        unsigned long long h = 1469598103934665603ull;
+        for (size_t i = 0; i < sizeof A; i++) { h ^= q[i]; h *= 1099511628211ull; }
+        fprintf(stderr, "[exhaustive] params hash %016llx blocks=%d\n", h, (int)std::min<u64>((A.n_total + EXH_WARPS - 1) / EXH_WARPS, (u64)sm_count * occ));
+    }
+    if (debug)
+        fprintf(stderr, "[exhaustive] U=%d slots=%llu  triples: bw=%d xch=%d items=%llu  pairs: bw=%d xch=%d items=%llu\n", U,
+                (unsigned long long)slots, A.p3.bw, A.p3.xch, (unsigned long long)A.n3, A.p2.bw, A.p2.xch, (unsigned long long)A.n2);
     if ((err = cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
     A.counter = sc->d_counter;
+    memcpy(sc->plan, &A, sizeof A);
+    sc->plan_valid = true; sc->plan_c = c; sc->plan_rb = rank_begin; sc->plan_re = rank_end;
     const int blocks = (int)std::min<u64>((A.n_total + EXH_WARPS - 1) / EXH_WARPS, (u64)sm_count * occ);
+    if (ev0 && (err = cudaEventRecord(ev0, stream)) != cudaSuccess) return (int)err;
     exhaustive_all_kernel<<<blocks, EXH_WARPS * 32, 0, stream>>>(L, A, Lg);
+    if (ev1 && (err = cudaEventRecord(ev1, stream)) != cudaSuccess) return (int)err;
     (*launches)++;
     return (int)cudaGetLastError();
 }
