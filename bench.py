@@ -292,6 +292,7 @@ def main():
             D.run_exhaustive_sharded(e, c, bounds=b, collective=coll)   # reset + this rank's launch + the combine step
             e.finalize()
 
+        e.flush_l2(); step()                  # first pass: builds the pair tables, allocates the scratch buffers
         l0 = e.launch_count()
         e.flush_l2(); step()
         launches_per_step = e.launch_count() - l0
