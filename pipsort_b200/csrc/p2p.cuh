@@ -9,7 +9,7 @@
 //              into its store, clears it, and writes `consumed = epoch` into every peer's control word (flow control: a
 //              peer may only push epoch k once the root has cleared the inbox of epoch k-1; peers poll their LOCAL word).
 // Both are ordinary stream-ordered launches: no host synchronisation, no collective library, and the only data that
-// crosses the links are the non-zero accumulator bins.  Spins are bounded (a few seconds of clock64) and raise
+// crosses the links are the non-zero accumulator bins.  Spins are bounded (about a minute of clock64) and raise
 // ERR_P2P_TIMEOUT instead of hanging the device.
 #pragma once
 #include "common.cuh"
@@ -19,7 +19,7 @@ namespace pipsort {
 typedef unsigned long long u64;
 
 constexpr int P2P_MAX_WORLD = 16;
-constexpr long long P2P_SPIN_CYCLES = 6000000000ll;   // ~3 s at 1.9 GHz
+constexpr long long P2P_SPIN_CYCLES = 120000000000ll;   // ~60 s at 1.9 GHz: ranks may reach the combine step far apart
 
 struct P2PPeers {
     u64* ctrl[P2P_MAX_WORLD];   // every rank's control words: [0] arrivals (root's is used), [1] consumed, [2] epoch (local)
