@@ -354,8 +354,13 @@ def main():
         h2d = sig.numel() * 8 + z.numel() * 8 + L.snp_map.size * 4 * 3 + 2 * 16
         d2h = 8 * (1 + 2 + L.N + 3 * L.U)
 
+        sig_np, z_np = sig.numpy(), z.numpy()
+
         def once():
-            e = P.Engine(L.num_snps, sig.numpy(), z.numpy(), L.d, L.K, L.snp_map, gamma=L.gamma,
+            if world == 1:      # one locus, one C-ABI call: create (H2D) + exhaustive pass + read (D2H) + destroy
+                return P.posterior_exhaustive(L.num_snps, sig_np, z_np, L.d, L.K, L.snp_map, c, gamma=L.gamma,
+                                              sharing_param=L.sharing_param, device=local)
+            e = P.Engine(L.num_snps, sig_np, z_np, L.d, L.K, L.snp_map, gamma=L.gamma,
                          sharing_param=L.sharing_param, max_causal=c, device=local)
             if world > 1:
                 D.bind_engine_to_current_stream(e)

@@ -172,6 +172,13 @@ int pipsort_last_kernel_ms(pipsort_engine* e, float* ms);
 /* Number of expanded configurations accumulated since the last reset (the reference's mycount). */
 int pipsort_config_count(pipsort_engine* e, uint64_t* out);
 
+/* One locus, one call: what Model::run does with a fresh PostCal (model.h:265-276: new PostCal, findOptimalSetGreedy ->
+ * computeTotalLikelihood, read the result members) -- pipsort_create + pipsort_run_exhaustive over the whole rank space +
+ * pipsort_read_accumulators + pipsort_destroy.  Host buffers in (locus), host buffers out (out); n_configs (optional)
+ * receives the reference's mycount.                                                                    */
+int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_t flags, int c, const pipsort_outputs* out,
+                                 uint64_t* n_configs);
+
 /* The same count as it was when pipsort_read_accumulators last ran (it travels with the results: no extra device
  * round trip).                                                                                     */
 int pipsort_last_read_config_count(const pipsort_engine* e, uint64_t* out);

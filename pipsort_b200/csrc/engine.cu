@@ -181,6 +181,8 @@ struct pipsort_engine {
     std::vector<int> loc[2];        // internal union index -> study-local index or -1
     std::vector<int> types;         // internal union index -> 0 shared, 1 only study 0, 2 only study 1, 3 nowhere
     std::vector<void*> allocs;
+    char* arena = nullptr;          // one allocation for (nearly) all device arrays of the engine
+    size_t arena_cap = 0, arena_off = 0;
     int* d_snp_map = nullptr;       // user order, [2][U]
     double* d_res = nullptr;
     std::vector<double> h_res;
@@ -259,10 +261,19 @@ int pool_setup(int device) {
     return 0;
 }
 
+// Device memory of an engine comes from ONE stream-ordered allocation made in pipsort_create (an arena with a bump
+// pointer): a locus needs ~25 arrays, and 25 cudaMallocAsync / cudaFreeAsync pairs are a visible part of a 0.3 ms
+// create-run-read-destroy cycle.  Requests the arena cannot hold (its size is an estimate) fall back to the pool.
 template <class T>
 int dev_alloc(pipsort_engine* e, T** p, size_t count) {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (e->arena && e->arena_off + bytes <= e->arena_cap) {
+        *p = reinterpret_cast<T*>(e->arena + e->arena_off);
+        e->arena_off += bytes;
+        return 0;
+    }
     void* q = nullptr;
-    CU(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), e->own_stream));
+    CU(cudaMallocAsync(&q, bytes, e->own_stream));
     e->allocs.push_back(q);
     *p = static_cast<T*>(q);
     return 0;
@@ -316,9 +327,11 @@ void pipsort_destroy(pipsort_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->own_stream) {
-        if (e->exh.d_prefix) cudaFreeAsync(e->exh.d_prefix, e->own_stream);
-        if (e->exh.d_counter) cudaFreeAsync(e->exh.d_counter, e->own_stream);
+        auto in_arena = [&](const void* q) { return e->arena && (const char*)q >= e->arena && (const char*)q < e->arena + e->arena_cap; };
+        if (e->exh.d_prefix && !in_arena(e->exh.d_prefix)) cudaFreeAsync(e->exh.d_prefix, e->own_stream);
+        if (e->exh.d_counter && !in_arena(e->exh.d_counter)) cudaFreeAsync(e->exh.d_counter, e->own_stream);
         for (void* p : e->allocs) cudaFreeAsync(p, e->own_stream);   // stream-ordered: no second synchronisation needed
+        if (e->arena) cudaFreeAsync(e->arena, e->own_stream);
     }
     {
         pipsort_engine::Sss& q = e->sss;
@@ -409,6 +422,24 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         }
     }
 
+    // ---- arena: everything dev_alloc hands out below (estimate; the accumulator store is sized for 16 bins) ------------
+    {
+        size_t est = 64 * 256 + sizeof(LocusDev) + (size_t)(3 + 5 * U + NCOUNTER) * 8 + (size_t)(U + 2) * 8 +
+                     ((size_t)NSLOT * 16 * (size_t)std::max((U + 3) & ~3, 4) + NCOUNTER) * 8;
+        size_t nints = (size_t)5 * U;
+        for (int s = 0; s < S; s++) {
+            const size_t nr = (size_t)lc->num_snps[s], n = e->orig[s].size(), ldw = (n + 3) & ~(size_t)3;
+            nints += 2 * n + nr;
+            est += (7 * nr + n * ldw) * 8;                                        // z upload, six vectors, W
+            if (lc->max_causal >= 2 && n <= 4096) est += n * ldw * 8;             // pair table (first exhaustive run)
+            if (nr * nr * 8 <= ((size_t)4 << 20)) est += nr * nr * 8 + 256;        // small raw LD upload buffer
+        }
+        est += nints * 4;
+        CU(cudaMallocAsync((void**)&e->arena, est, e->own_stream));
+        e->arena_cap = est;
+        e->arena_off = 0;
+    }
+
     // ---- device copy of the locus -------------------------------------------------------------------
     LocusDev& L = e->L;
     memset(&L, 0, sizeof L);
@@ -447,11 +478,18 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     double K_total = (flags & PIPSORT_RAW_LD) ? 0.0 : lc->K;
     // all host -> device copies of the caller's buffers first, then one event: pipsort_create returns when they are done
     double *up_sigma[2] = {nullptr, nullptr}, *up_z[2] = {nullptr, nullptr};
+    bool up_sigma_temp[2] = {false, false};
     {
         size_t so = 0, zo = 0;
         for (int s = 0; s < S; s++) {
             const size_t nr = (size_t)lc->num_snps[s];
-            CU(cudaMallocAsync(&up_sigma[s], std::max<size_t>(nr * nr, 1) * sizeof(double), e->stream));
+            if (nr * nr * 8 <= ((size_t)4 << 20)) {          // small: from the arena (stays allocated, a few hundred KB)
+                if ((rc = dev_alloc(e, &up_sigma[s], nr * nr))) return rc;
+                up_sigma_temp[s] = false;
+            } else {
+                CU(cudaMallocAsync(&up_sigma[s], std::max<size_t>(nr * nr, 1) * sizeof(double), e->stream));
+                up_sigma_temp[s] = true;
+            }
             CU(cudaMemcpyAsync(up_sigma[s], lc->sigma + so, nr * nr * sizeof(double), cudaMemcpyHostToDevice, e->stream));
             if ((rc = dev_upload(e, &up_z[s], lc->z + zo, nr))) return rc;
             so += nr * nr; zo += nr;
@@ -471,7 +509,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         if (flags & PIPSORT_RAW_LD) {   // model.h:171-264 on the device: PSD shift + eigen-decomposition -> effective LD, K_s
             std::string why;
             const int prc = prep_study_device(e->stream, n_raw, d_sigma, d_zraw, &e->prep[s], &why, &e->launches);
-            if (prc) { cudaFreeAsync(d_sigma, e->stream); return fail(prc == -3 ? PIPSORT_E_RANGE : PIPSORT_E_CUDA, "pre-processing of study %d: %s", s, why.c_str()); }
+            if (prc) { if (up_sigma_temp[s]) cudaFreeAsync(d_sigma, e->stream); return fail(prc == -3 ? PIPSORT_E_RANGE : PIPSORT_E_CUDA, "pre-processing of study %d: %s", s, why.c_str()); }
             K_total += e->prep[s].K;
             e->prepped = true;
         }
@@ -488,7 +526,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             e->launches += 2;
         }
         CU(cudaGetLastError());
-        CU(cudaFreeAsync(d_sigma, e->stream));
+        if (up_sigma_temp[s]) CU(cudaFreeAsync(d_sigma, e->stream));
         StudyDev& st = L.st[s];
         st.W = W; st.A = A; st.z = z; st.invA = invA; st.u = u; st.e1m = e1m; st.e1n = e1n;
         st.n = n; st.ldw = ldw; st.hd = 0.5 * d;
@@ -581,6 +619,10 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     acc.counters = acc.bins + (e->bins_len - NCOUNTER);
     if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U + NCOUNTER))) return rc;   // results | counters: one D2H per read
     e->h_res.resize(3 + (size_t)5 * U + NCOUNTER);
+    // scratch of the exhaustive launch (work-queue head, per-a item prefix) from the arena as well
+    if ((rc = dev_alloc(e, &e->exh.d_counter, 1))) return rc;
+    e->exh.cap_prefix = (size_t)U + 2;
+    if ((rc = dev_alloc(e, &e->exh.d_prefix, e->exh.cap_prefix))) return rc;
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
     // the caller's buffers and the local staging vectors must not be read after return: wait for the H2D copies only
     // (recorded in ev_up after the last of them); the preparation kernels and memsets keep running asynchronously.
@@ -728,8 +770,7 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
         for (int s = 0; s < 2; s++) {
             StudyDev& st = e->L.st[s];
             double* P = nullptr;
-            CU(cudaMallocAsync(&P, (size_t)std::max(st.n, 1) * std::max(st.ldw, 1) * sizeof(double), e->stream));
-            e->allocs.push_back(P);
+            if ((rc = dev_alloc(e, &P, (size_t)std::max(st.n, 1) * std::max(st.ldw, 1)))) return rc;
             if (st.n > 0) {
                 dim3 grid((st.ldw + 127) / 128, st.n);
                 pair_table_kernel<<<grid, 128, 0, e->stream>>>(st, P);
@@ -1058,6 +1099,23 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
         if (out->notSharedLL) out->notSharedLL[ug] = r[(size_t)4 * U + g];
     }
     return 0;
+}
+
+int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_t flags, int c, const pipsort_outputs* out,
+                                 uint64_t* n_configs) {
+    if (!out) return fail(PIPSORT_E_ARG, "null argument");
+    pipsort_engine* e = nullptr;
+    int rc = pipsort_create(locus, device, flags, &e);
+    if (rc) return rc;
+    uint64_t total = 0;
+    rc = pipsort_total_ranks(e, c, &total);
+    if (!rc) rc = pipsort_run_exhaustive(e, c, 0, total);
+    if (!rc) rc = pipsort_read_accumulators(e, out);
+    if (!rc && n_configs) *n_configs = e->last_read_count;
+    std::string keep = g_err;
+    pipsort_destroy(e);
+    g_err = keep;
+    return rc;
 }
 
 int pipsort_last_read_config_count(const pipsort_engine* e, uint64_t* out) {

@@ -92,9 +92,11 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     const int U = L.U;
     cudaError_t err;
     static_assert(sizeof(ExhAll) <= sizeof(sc->plan), "plan cache too small");
-    if (!sc->d_counter) {
-        if ((err = cudaMallocAsync(&sc->d_counter, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
-        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sc->occ, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
+    if (!sc->d_counter && (err = cudaMallocAsync(&sc->d_counter, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
+    if (!sc->occ) {
+        static int occ_cache = 0;    // a property of the kernel and the device generation: query once per process
+        if (!occ_cache && (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
+        sc->occ = occ_cache;
     }
     ExhAll A;
     const bool knobs = getenv("PIPSORT_EXH_BW") || getenv("PIPSORT_EXH_ITEMS_PER_SLOT");   // experiments: plan afresh
@@ -164,7 +166,7 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         if (!(sc->k_U == U && sc->k_bw == P.bw && sc->k_xch == P.xch && sc->k_alo == P.a_lo && sc->k_ahi == P.a_hi)) {
             prefix.push_back(0);
             for (int a = P.a_lo; a <= P.a_hi; a++) prefix.push_back(prefix.back() + exh_items_of(U, a, P.bw, P.xch));
-            if (sc->cap_prefix < prefix.size()) {
+            if (sc->cap_prefix < prefix.size()) {     // (never for a buffer that came from the engine's arena: U + 2 entries)
                 if (sc->d_prefix) cudaFreeAsync(sc->d_prefix, stream);
                 sc->cap_prefix = prefix.size() * 2;
                 if ((err = cudaMallocAsync(&sc->d_prefix, sc->cap_prefix * sizeof(u64), stream)) != cudaSuccess) return (int)err;

@@ -60,6 +60,7 @@ def lib():
         L.pipsort_preprocess_study.argtypes = [i32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                                C.POINTER(C.c_double), C.POINTER(_PrepInfo)]
         L.pipsort_prep_info_get.argtypes = [vp, i32, C.POINTER(_PrepInfo)]
+        L.pipsort_posterior_exhaustive.argtypes = [C.POINTER(_Locus), i32, C.c_uint32, i32, C.POINTER(_Outputs), C.POINTER(u64)]
         L.pipsort_destroy.argtypes = [vp]
         L.pipsort_destroy.restype = None
         L.pipsort_reset.argtypes = [vp]
@@ -367,6 +368,30 @@ class Engine:
 
     def launch_count(self):
         return int(lib().pipsort_launch_count(self._h))
+
+
+def posterior_exhaustive(num_snps, sigma, z, d, K, snp_map, c, gamma=0.01, sharing_param=0.75, device=0, raw_ld=False):
+    """One locus, one call (pipsort_posterior_exhaustive): host arrays in, Results out -- what Model::run does with a fresh
+    PostCal.  sigma / z: flat float64 arrays, studies concatenated (or lists of per-study arrays)."""
+    num_snps = np.ascontiguousarray(num_snps, dtype=np.int32)
+    if isinstance(sigma, (list, tuple)):
+        sigma = np.concatenate([np.asarray(s, dtype=np.float64).ravel() for s in sigma])
+    if isinstance(z, (list, tuple)):
+        z = np.concatenate([np.asarray(v, dtype=np.float64).ravel() for v in z])
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64).ravel()
+    z = np.ascontiguousarray(z, dtype=np.float64).ravel()
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    smap = np.ascontiguousarray(snp_map, dtype=np.int32)
+    S, U, N = len(num_snps), int(smap.shape[1]), int(num_snps.sum())
+    loc = _Locus(S, num_snps.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sigma), _dp(z), _dp(d), float(K), U,
+                 smap.ctypes.data_as(C.POINTER(C.c_int32)), float(gamma), float(sharing_param), int(c))
+    buf = np.zeros(1 + N + S + 3 * U)
+    total, post, nc = buf[0:1], buf[1:1 + N], buf[1 + N:1 + N + S]
+    sp, sl, nl = buf[1 + N + S:1 + N + S + U], buf[1 + N + S + U:1 + N + S + 2 * U], buf[1 + N + S + 2 * U:]
+    o = _Outputs(_dp(total), _dp(post), _dp(nc), _dp(sp), _dp(sl), _dp(nl))
+    cnt = C.c_uint64()
+    _check(lib().pipsort_posterior_exhaustive(C.byref(loc), int(device), RAW_LD if raw_ld else 0, int(c), C.byref(o), C.byref(cnt)))
+    return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
 
 
 def preprocess_study(ld, z, device=0):

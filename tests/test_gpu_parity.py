@@ -301,3 +301,13 @@ def test_baseline_config_b_150_snps_c3_sampled_against_oracle():
         r = e.compute_total_likelihood(3)
     assert r.n_configs == want_n == 12197751
     assert r.total == pytest.approx(want_total, rel=1e-10)
+
+
+def test_one_call_posterior_matches_engine_path():
+    """pipsort_posterior_exhaustive (create + run + read + destroy in one C-ABI call) == the step-by-step path."""
+    import pipsort_b200 as P
+    g = golden("example_c2_p025")
+    L = oracle_locus("example", p=0.25)
+    r = P.posterior_exhaustive(L.n_snps, L.sigma, L.z, L.d, L.K, L.snp_map, 2, gamma=L.gamma, sharing_param=L.p)
+    assert r.n_configs == 216817
+    assert_results_match(r, g)
