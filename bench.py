@@ -43,8 +43,8 @@ WORKLOADS = {
     "B1500c3": (1500, 0.8, 3),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one exhaustive_all_kernel launch, from the `ncu --set full` captures
-# summarised in profiles/r1_v5_exhaustive_all_*.txt (the loci are L2 resident: LD and the pair tables are read from HBM once)
-TRAFFIC_BYTES = {"B150c3": 803072 + 256, "B1500c3": 39069440 + 998144}
+# summarised in profiles/r1_v6_exhaustive_all_*.txt (the loci are L2 resident: LD and the pair tables are read from HBM once)
+TRAFFIC_BYTES = {"B150c3": 790528 + 0, "B1500c3": 39675904 + 940800}
 METRIC = "causal configurations/sec (exhaustive, c=3, synthetic 150-SNP/study two-ancestry locus)"
 UNIT = "configs/s"
 

@@ -4,6 +4,7 @@
 // score.cuh (generic, warp per union configuration) and exhaustive.cuh (register kernel, lane per
 // union subset).  No CPU compute path exists: without a usable CUDA device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1104,17 +1105,28 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
 int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_t flags, int c, const pipsort_outputs* out,
                                  uint64_t* n_configs) {
     if (!out) return fail(PIPSORT_E_ARG, "null argument");
+    static const bool trace = getenv("PIPSORT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto t0 = now();
     pipsort_engine* e = nullptr;
     int rc = pipsort_create(locus, device, flags, &e);
     if (rc) return rc;
+    const auto t1 = now();
     uint64_t total = 0;
     rc = pipsort_total_ranks(e, c, &total);
     if (!rc) rc = pipsort_run_exhaustive(e, c, 0, total);
+    const auto t2 = now();
     if (!rc) rc = pipsort_read_accumulators(e, out);
+    const auto t3 = now();
     if (!rc && n_configs) *n_configs = e->last_read_count;
     std::string keep = g_err;
     pipsort_destroy(e);
     g_err = keep;
+    if (trace) {
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[pipsort] create %.1f us, run (enqueue) %.1f us, read (incl. device time) %.1f us, destroy %.1f us\n", us(t0, t1),
+                us(t1, t2), us(t2, t3), us(t3, now()));
+    }
     return rc;
 }
 
