@@ -26,6 +26,8 @@
 
 using namespace pipsort;
 
+#define PIPSORT_INTERNAL_NO_UPLOAD_WAIT 0x80000000u   /* not part of the public flag set */
+
 namespace {
 
 thread_local std::string g_err;
@@ -58,35 +60,51 @@ u64 binom_host(int n, int k, bool* overflow) {
 }
 
 // ---- preparation kernels ------------------------------------------------------------------------------
-// W[i][j] = d * sigma[orig[i]][orig[j]]  (permutation into the internal order + the d_s scaling of
-// construct_diagC's diagonal, postcal.cpp:89,250,254-255)
-__global__ void gather_study_kernel(const double* __restrict__ sigma, int n_raw, const int* __restrict__ orig, int n,
-                                    int ldw, double d, double* __restrict__ W) {
+// W[i][j] = d * sigma[orig[i]][orig[j]]  (permutation into the internal order + the d_s scaling of construct_diagC's
+// diagonal, postcal.cpp:89,250,254-255) and the per-SNP vectors A = 1 + W_ii, z, 1/A, z/A, E_s({i}) = e1m 2^e1n,
+// for BOTH studies in one launch (blockIdx.z = study): a locus that takes 60 us to evaluate should not
+// spend 20 us on four tiny preparation launches.  Thread j == 0 of row i also fills the per-SNP vectors of i.
+struct PrepStudyArgs {
+    const double* sigma; const double* z_raw; const int* orig;
+    int n_raw, n, ldw;
+    double d;
+    double *W, *A, *z, *invA, *u, *e1m;
+    int* e1n;
+};
+struct PrepLocusArgs { PrepStudyArgs s[2]; };
+
+__global__ void __launch_bounds__(128) prepare_locus_kernel(PrepLocusArgs P) {
+    const PrepStudyArgs& S = P.s[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
-    if (j >= ldw || i >= n) return;
+    if (j >= S.ldw || i >= S.n) return;
+    const int oi = S.orig[i];
     double v = 0.0;
-    if (j < n) v = d * sigma[(size_t)orig[i] * n_raw + orig[j]];
-    W[(size_t)i * ldw + j] = v;
+    if (j < S.n) v = S.d * S.sigma[(size_t)oi * S.n_raw + S.orig[j]];
+    S.W[(size_t)i * S.ldw + j] = v;
+    if (j == 0) {
+        const double a = 1.0 + S.d * S.sigma[(size_t)oi * S.n_raw + oi];
+        const double zi = S.z_raw[oi];
+        S.A[i] = a;
+        S.z[i] = zi;
+        S.invA[i] = 1.0 / a;
+        S.u[i] = zi / a;
+        double m;
+        int e;
+        xexp(0.5 * S.d * (zi * zi / a), m, e);
+        S.e1m[i] = m / sqrt(a);
+        S.e1n[i] = e;
+    }
 }
 
-__global__ void study_vectors_kernel(const double* __restrict__ W, int ldw, const double* __restrict__ z_raw,
-                                     const int* __restrict__ orig, int n, double hd, double* __restrict__ A,
-                                     double* __restrict__ z, double* __restrict__ invA, double* __restrict__ u,
-                                     double* __restrict__ e1m, int* __restrict__ e1n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double a = 1.0 + W[(size_t)i * ldw + i];
-    const double zi = z_raw[orig[i]];
-    A[i] = a;
-    z[i] = zi;
-    invA[i] = 1.0 / a;
-    u[i] = zi / a;
-    double m;
-    int e;
-    xexp(hd * (zi * zi / a), m, e);
-    e1m[i] = m / sqrt(a);
-    e1n[i] = e;
+struct PairTablesArgs { StudyDev st[2]; double* P[2]; };
+__global__ void __launch_bounds__(128) pair_tables_kernel(PairTablesArgs T) {   // pair_table_kernel for both studies
+    const StudyDev& S = T.st[blockIdx.z];
+    double* __restrict__ P = T.P[blockIdx.z];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= S.ldw || i >= S.n) return;
+    P[(size_t)i * S.ldw + j] = pair_table_entry(S, i, j);
 }
 
 // ---- finalize: bins -> log-space results --------------------------------------------------------------
@@ -182,11 +200,15 @@ struct pipsort_engine {
     std::vector<int> loc[2];        // internal union index -> study-local index or -1
     std::vector<int> types;         // internal union index -> 0 shared, 1 only study 0, 2 only study 1, 3 nowhere
     std::vector<void*> allocs;
+    char* pin = nullptr;            // pinned staging buffer of the stream kit (PIN_BYTES), bump-allocated, never reused
+    size_t pin_off = 0;             // within an engine's life: an asynchronous copy may still be reading a slice
+    bool defer_upload_sync = false; // one-call path: the caller's buffers outlive the call, no wait after the uploads
     char* arena = nullptr;          // one allocation for (nearly) all device arrays of the engine
     size_t arena_cap = 0, arena_off = 0;
     int* d_snp_map = nullptr;       // user order, [2][U]
     double* d_res = nullptr;
     std::vector<double> h_res;
+    double* h_res_pin = nullptr;    // slice of the pinned staging buffer for the result read-back
     size_t bins_len = 0;
     u64 launches = 0;
     // scratch for pipsort_score_union_configs (host buffers)
@@ -228,7 +250,8 @@ namespace {
 // are created and destroyed once per locus).
 // Streams and timing events are recycled across engines of one process (a fine-mapping run creates and destroys one
 // engine per locus; cudaStreamCreate / cudaEventCreate are a measurable part of a 0.1 ms locus).
-struct StreamKit { cudaStream_t stream; cudaEvent_t ev[5]; };
+constexpr size_t PIN_BYTES = (size_t)256 << 10;   // pinned staging per kit: small uploads / the result read-back go through it
+struct StreamKit { cudaStream_t stream; cudaEvent_t ev[5]; char* pin; };
 std::vector<StreamKit>& kit_cache(int device) {
     static std::vector<StreamKit> cache[64];
     return cache[device & 63];
@@ -244,6 +267,8 @@ int kit_acquire(int device, StreamKit* k) {
     CU(cudaStreamCreateWithFlags(&k->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 4; i++) CU(cudaEventCreate(&k->ev[i]));
     CU(cudaEventCreateWithFlags(&k->ev[4], cudaEventDisableTiming));
+    k->pin = nullptr;
+    if (cudaHostAlloc((void**)&k->pin, PIN_BYTES, cudaHostAllocDefault) != cudaSuccess) { k->pin = nullptr; cudaGetLastError(); }
     return 0;
 }
 void kit_release(int device, const StreamKit& k) {
@@ -285,6 +310,24 @@ int dev_upload(pipsort_engine* e, T** p, const T* src, size_t count) {
     int rc = dev_alloc(e, p, count);
     if (rc) return rc;
     if (count) CU(cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+
+// a slice of the pinned staging buffer, or nullptr when it is used up (callers then copy from pageable memory)
+char* pin_slice(pipsort_engine* e, size_t bytes) {
+    bytes = (bytes + 63) & ~(size_t)63;
+    if (!e->pin || e->pin_off + bytes > PIN_BYTES) return nullptr;
+    char* p = e->pin + e->pin_off;
+    e->pin_off += bytes;
+    return p;
+}
+
+// host -> device copy of a small host array that may disappear after the call: staged through pinned memory so that the
+// copy is truly asynchronous (a pageable source makes cudaMemcpyAsync block for several microseconds each time)
+int upload_small(pipsort_engine* e, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return 0;
+    if (char* st = pin_slice(e, bytes)) { memcpy(st, src, bytes); src = st; }
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream));
     return 0;
 }
 
@@ -351,7 +394,7 @@ void pipsort_destroy(pipsort_engine* e) {
     if (e->d_upd) cudaFree(e->d_upd);
     if (e->d_out) cudaFree(e->d_out);
     if (e->own_stream && e->ev0 && e->ev1 && e->evk0 && e->evk1 && e->ev_up) {   // back to the per-device cache
-        StreamKit k{e->own_stream, {e->ev0, e->ev1, e->evk0, e->evk1, e->ev_up}};
+        StreamKit k{e->own_stream, {e->ev0, e->ev1, e->evk0, e->evk1, e->ev_up}, e->pin};
         if (e->l2_scratch) cudaFree(e->l2_scratch);
         kit_release(e->device, k);
         delete e;
@@ -370,13 +413,19 @@ void pipsort_destroy(pipsort_engine* e) {
 
 static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pipsort_engine* e) {
     const int S = lc->num_studies, U = lc->union_count;
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    static int ndev = -1;
+    if (ndev <= 0 && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) {
+        ndev = -1;
         return fail(PIPSORT_E_CUDA, "no CUDA device available (the engine has no CPU path)");
+    }
     if (device < 0 || device >= ndev) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev);
     CU(cudaSetDevice(device));
     e->device = device;
-    CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        static int sm_cache[64] = {0};
+        if (!sm_cache[device & 63]) CU(cudaDeviceGetAttribute(&sm_cache[device & 63], cudaDevAttrMultiProcessorCount, device));
+        e->sm_count = sm_cache[device & 63];
+    }
     {
         int rcp = pool_setup(device);
         if (rcp) return rcp;
@@ -386,6 +435,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         int rck = kit_acquire(device, &k);
         if (rck) return rck;
         e->own_stream = k.stream; e->ev0 = k.ev[0]; e->ev1 = k.ev[1]; e->evk0 = k.ev[2]; e->evk1 = k.ev[3]; e->ev_up = k.ev[4];
+        e->pin = k.pin; e->pin_off = 0;
     }
     e->stream = e->own_stream;
     e->U = U;
@@ -469,7 +519,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             for (int i = 0; i < U; i++) if (e->loc[s][i] >= 0) l2u[e->loc[s][i]] = i;
             pack.insert(pack.end(), l2u.begin(), l2u.end());
         }
-        if ((rc = dev_upload(e, &d_ints, pack.data(), pack.size()))) return rc;
+        if ((rc = dev_alloc(e, &d_ints, pack.size())) || (rc = upload_small(e, d_ints, pack.data(), pack.size() * sizeof(int)))) return rc;
     }
     L.u2i = d_ints;
     for (int s = 0; s < S; s++) { L.raw2loc[s] = d_ints + r2l_off[s]; L.loc2u[s] = d_ints + l2u_off[s]; L.n_raw[s] = lc->num_snps[s]; }
@@ -497,6 +547,8 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         }
         CU(cudaEventRecord(e->ev_up, e->stream));
     }
+    PrepLocusArgs prep_args;
+    memset(&prep_args, 0, sizeof prep_args);
     for (int s = 0; s < S; s++) {
         const int n_raw = lc->num_snps[s], n = (int)e->orig[s].size();
         const int ldw = (n + 3) & ~3;
@@ -520,14 +572,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         if ((rc = dev_alloc(e, &A, n)) || (rc = dev_alloc(e, &z, n)) || (rc = dev_alloc(e, &invA, n)) ||
             (rc = dev_alloc(e, &u, n)) || (rc = dev_alloc(e, &e1m, n)) || (rc = dev_alloc(e, &e1n, n)))
             return rc;
-        if (n > 0) {
-            dim3 grid((ldw + 127) / 128, n);
-            gather_study_kernel<<<grid, 128, 0, e->stream>>>(d_sigma, n_raw, d_orig, n, ldw, d, W);
-            study_vectors_kernel<<<(n + 127) / 128, 128, 0, e->stream>>>(W, ldw, d_zraw, d_orig, n, 0.5 * d, A, z, invA, u, e1m, e1n);
-            e->launches += 2;
-        }
-        CU(cudaGetLastError());
-        if (up_sigma_temp[s]) CU(cudaFreeAsync(d_sigma, e->stream));
+        prep_args.s[s] = PrepStudyArgs{d_sigma, d_zraw, d_orig, n_raw, n, ldw, d, W, A, z, invA, u, e1m, e1n};
         StudyDev& st = L.st[s];
         st.W = W; st.A = A; st.z = z; st.invA = invA; st.u = u; st.e1m = e1m; st.e1n = e1n;
         st.n = n; st.ldw = ldw; st.hd = 0.5 * d;
@@ -548,6 +593,18 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         minexp_bits -= 0.5 * e->kb * std::log2(1.0 + d * maxdiag);
         soff += (size_t)n_raw * n_raw;
         zoff += n_raw;
+    }
+
+    {   // W = d Sigma~ in the internal order + the per-SNP vectors, both studies, one launch
+        const int nmax = std::max(prep_args.s[0].n, prep_args.s[1].n), lmax = std::max(prep_args.s[0].ldw, prep_args.s[1].ldw);
+        if (nmax > 0) {
+            dim3 grid((lmax + 127) / 128, nmax, 2);
+            prepare_locus_kernel<<<grid, 128, 0, e->stream>>>(prep_args);
+            e->launches++;
+            CU(cudaGetLastError());
+        }
+        for (int s = 0; s < S; s++)
+            if (up_sigma_temp[s]) CU(cudaFreeAsync(up_sigma[s], e->stream));
     }
 
     // ---- prior tables (log_prior, postcal.cpp:19-59) --------------------------------------------------
@@ -624,13 +681,15 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     if ((rc = dev_alloc(e, &e->exh.d_counter, 1))) return rc;
     e->exh.cap_prefix = (size_t)U + 2;
     if ((rc = dev_alloc(e, &e->exh.d_prefix, e->exh.cap_prefix))) return rc;
+    e->exh.pin_prefix_cap = e->exh.cap_prefix * sizeof(u64);
+    e->exh.pin_prefix = pin_slice(e, e->exh.pin_prefix_cap);
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
     // the caller's buffers and the local staging vectors must not be read after return: wait for the H2D copies only
     // (recorded in ev_up after the last of them); the preparation kernels and memsets keep running asynchronously.
     // e->L lives as long as the engine, so its upload needs no wait.
     e->L_host_copy = e->L;
-    if ((rc = dev_upload(e, &e->d_L, &e->L_host_copy, 1))) return rc;
-    CU(cudaEventSynchronize(e->ev_up));
+    if ((rc = dev_alloc(e, &e->d_L, 1)) || (rc = upload_small(e, e->d_L, &e->L_host_copy, sizeof(LocusDev)))) return rc;
+    if (!e->defer_upload_sync) CU(cudaEventSynchronize(e->ev_up));
     return 0;
 }
 
@@ -643,6 +702,7 @@ int pipsort_create(const pipsort_locus* lc, int device, uint32_t flags, pipsort_
         return fail(PIPSORT_E_ARG, "incomplete locus description");
     if (lc->num_snps[0] < 0 || lc->num_snps[1] < 0) return fail(PIPSORT_E_ARG, "negative SNP count");
     pipsort_engine* e = new pipsort_engine();
+    e->defer_upload_sync = (flags & PIPSORT_INTERNAL_NO_UPLOAD_WAIT) != 0;
     int rc = create_impl(lc, device, flags, e);
     if (rc) { std::string keep = g_err; pipsort_destroy(e); g_err = keep; return rc; }
     *out = e;
@@ -768,20 +828,24 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     if (jreg >= 2 && !e->L.st[0].P) {
         // first exhaustive run with pairs / triples: build the pair tables E_s{i,j} (n_s^2 doubles per study, once)
         if (e->capturing) return fail(PIPSORT_E_ARG, "run the pass once before capturing it (the first run builds the pair tables)");
+        PairTablesArgs pt;
         for (int s = 0; s < 2; s++) {
             StudyDev& st = e->L.st[s];
             double* P = nullptr;
             if ((rc = dev_alloc(e, &P, (size_t)std::max(st.n, 1) * std::max(st.ldw, 1)))) return rc;
-            if (st.n > 0) {
-                dim3 grid((st.ldw + 127) / 128, st.n);
-                pair_table_kernel<<<grid, 128, 0, e->stream>>>(st, P);
-                e->launches++;
-            }
+            pt.st[s] = st;
+            pt.P[s] = P;
             st.P = P;
+        }
+        const int nmax = std::max(pt.st[0].n, pt.st[1].n), lmax = std::max(pt.st[0].ldw, pt.st[1].ldw);
+        if (nmax > 0) {
+            dim3 grid((lmax + 127) / 128, nmax, 2);
+            pair_tables_kernel<<<grid, 128, 0, e->stream>>>(pt);
+            e->launches++;
         }
         CU(cudaGetLastError());
         e->L_host_copy = e->L;
-        CU(cudaMemcpyAsync(e->d_L, &e->L_host_copy, sizeof(LocusDev), cudaMemcpyHostToDevice, e->stream));
+        if ((rc = upload_small(e, e->d_L, &e->L_host_copy, sizeof(LocusDev)))) return rc;
     }
     if (jreg >= 0) {
         const bool timed = jdom <= jreg && !e->capturing;
@@ -1074,12 +1138,14 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
     int rcf = pipsort_finalize(e);
     if (rcf) return rcf;
     const int U = e->U;
-    CU(cudaMemcpyAsync(e->h_res.data(), e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (!e->h_res_pin) e->h_res_pin = reinterpret_cast<double*>(pin_slice(e, e->h_res.size() * sizeof(double)));
+    double* hres = e->h_res_pin ? e->h_res_pin : e->h_res.data();
+    CU(cudaMemcpyAsync(hres, e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    int rc = flags_to_error(e->h_res.data() + 3 + (size_t)5 * U);
+    int rc = flags_to_error(hres + 3 + (size_t)5 * U);
     if (rc) return rc;
-    e->last_read_count = (uint64_t)e->h_res[3 + (size_t)5 * U];
-    const double* r = e->h_res.data();
+    e->last_read_count = (uint64_t)hres[3 + (size_t)5 * U];
+    const double* r = hres;
     if (out->total) *out->total = r[0];
     if (out->noCausal) { out->noCausal[0] = r[1]; out->noCausal[1] = r[2]; }
     r += 3;
@@ -1109,7 +1175,8 @@ int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_
     auto now = [] { return std::chrono::steady_clock::now(); };
     const auto t0 = now();
     pipsort_engine* e = nullptr;
-    int rc = pipsort_create(locus, device, flags, &e);
+    // the caller's buffers stay valid until this function returns: no need to wait for the uploads inside create
+    int rc = pipsort_create(locus, device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT, &e);
     if (rc) return rc;
     const auto t1 = now();
     uint64_t total = 0;

@@ -21,6 +21,8 @@ struct ExhScratch {           // owned by the engine, reused across launches
     // key of the prefix table currently on the device
     int k_U = -1, k_bw = 0, k_xch = 0, k_alo = 0, k_ahi = 0;
     // the work decomposition of the last launch (a pass is usually repeated with the same c and rank range)
+    char* pin_prefix = nullptr;   // pinned staging slice for the FIRST prefix upload (later ones may overlap an in-flight copy)
+    size_t pin_prefix_cap = 0;
     bool plan_valid = false;
     int plan_c = 0;
     unsigned long long plan_rb = 0, plan_re = 0;
@@ -145,12 +147,17 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         const int xchs[] = {1 << 20, 32, 16, 12, 8, 6, 4, 3, 2, 1};
         u64 n = 0;
         bw = 32;
-        for (int x : xchs) {
-            xch = x;
-            n = count_items(bw, xch);
-            if (n + already >= (u64)per_slot * slots) return n;
+        xch = 1;
+        const u64 n1 = count_items(bw, 1);                     // the finest 32-wide decomposition: an upper bound
+        if (n1 + already >= (u64)per_slot * slots) {
+            for (int x : xchs) {
+                xch = x;
+                n = x == 1 ? n1 : count_items(bw, xch);
+                if (n + already >= (u64)per_slot * slots) return n;
+            }
         }
-        for (int w : {32, 16, 8}) {   // small locus: narrower windows only when full ones leave most warps without any item
+        if ((n1 + already) * 10 >= slots * 9) { bw = 32; xch = 1; return n1; }
+        for (int w : {16, 8}) {       // small locus: narrower windows only when full ones leave most warps without any item
             bw = w; xch = 1;          // (150 SNPs/study: 1678 items of (32,1) on 1776 warps beat 3020 items of (16,1))
             n = count_items(bw, xch);
             if ((n + already) * 10 >= slots * 9) break;
@@ -171,7 +178,13 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
                 sc->cap_prefix = prefix.size() * 2;
                 if ((err = cudaMallocAsync(&sc->d_prefix, sc->cap_prefix * sizeof(u64), stream)) != cudaSuccess) return (int)err;
             }
-            if ((err = cudaMemcpyAsync(sc->d_prefix, prefix.data(), prefix.size() * sizeof(u64), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)err;
+            const void* src = prefix.data();
+            if (sc->pin_prefix && prefix.size() * sizeof(u64) <= sc->pin_prefix_cap) {
+                memcpy(sc->pin_prefix, prefix.data(), prefix.size() * sizeof(u64));
+                src = sc->pin_prefix;
+                sc->pin_prefix = nullptr;      // one use
+            }
+            if ((err = cudaMemcpyAsync(sc->d_prefix, src, prefix.size() * sizeof(u64), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return (int)err;
             sc->k_U = U; sc->k_bw = P.bw; sc->k_xch = P.xch; sc->k_alo = P.a_lo; sc->k_ahi = P.a_hi;
         }
         P.item_prefix = sc->d_prefix;

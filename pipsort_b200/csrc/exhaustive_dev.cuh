@@ -100,10 +100,7 @@ __device__ __forceinline__ double extend_fast(double base, double hd, double r, 
 // per `a` (U times): n^2 exponentials here replace n^3/3 there.  Values outside the fast range (or a lost positive
 // definiteness) are stored as +inf: the kernel then sends the subset down its mantissa/exponent path, which also
 // raises the error flag where the reference would stop.
-__global__ void __launch_bounds__(128) pair_table_kernel(StudyDev S, double* __restrict__ P) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (j >= S.ldw || i >= S.n) return;
+__device__ __forceinline__ double pair_table_entry(const StudyDev& S, int i, int j) {
     double v = 0.0;
     if (j < S.n && j != i) {
         const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -118,7 +115,7 @@ __global__ void __launch_bounds__(128) pair_table_kernel(StudyDev S, double* __r
             if (!(v < FAST_LIMIT)) v = inf;
         }
     }
-    P[(size_t)i * S.ldw + j] = v;
+    return v;
 }
 
 constexpr __host__ __device__ bool in0(int t) { return t != 1; }   // state 0: study 0 only, 1: study 1 only, 2: both

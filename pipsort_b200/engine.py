@@ -37,6 +37,16 @@ class _Locus(C.Structure):
                 ("sharing_param", C.c_double), ("max_causal", C.c_int32)]
 
 
+class _LocusV(C.Structure):      # same layout as _Locus with untyped pointers: filled from ndarray.ctypes.data (cheap)
+    _fields_ = [("num_studies", C.c_int32), ("num_snps", C.c_void_p), ("sigma", C.c_void_p), ("z", C.c_void_p),
+                ("d", C.c_void_p), ("K", C.c_double), ("union_count", C.c_int32), ("snp_map", C.c_void_p),
+                ("gamma", C.c_double), ("sharing_param", C.c_double), ("max_causal", C.c_int32)]
+
+
+class _OutputsV(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("total", "postValues", "noCausal", "sharedPips", "sharedLL", "notSharedLL")]
+
+
 class _PrepInfo(C.Structure):
     _fields_ = [("add_diag", C.c_double), ("K", C.c_double), ("min_abs_eig", C.c_double), ("n_negative", C.c_int32),
                 ("psd_iterations", C.c_int32)]
@@ -60,7 +70,7 @@ def lib():
         L.pipsort_preprocess_study.argtypes = [i32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                                C.POINTER(C.c_double), C.POINTER(_PrepInfo)]
         L.pipsort_prep_info_get.argtypes = [vp, i32, C.POINTER(_PrepInfo)]
-        L.pipsort_posterior_exhaustive.argtypes = [C.POINTER(_Locus), i32, C.c_uint32, i32, C.POINTER(_Outputs), C.POINTER(u64)]
+        L.pipsort_posterior_exhaustive.argtypes = [C.POINTER(_LocusV), i32, C.c_uint32, i32, C.POINTER(_OutputsV), C.POINTER(u64)]
         L.pipsort_destroy.argtypes = [vp]
         L.pipsort_destroy.restype = None
         L.pipsort_reset.argtypes = [vp]
@@ -383,12 +393,13 @@ def posterior_exhaustive(num_snps, sigma, z, d, K, snp_map, c, gamma=0.01, shari
     d = np.ascontiguousarray(d, dtype=np.float64)
     smap = np.ascontiguousarray(snp_map, dtype=np.int32)
     S, U, N = len(num_snps), int(smap.shape[1]), int(num_snps.sum())
-    loc = _Locus(S, num_snps.ctypes.data_as(C.POINTER(C.c_int32)), _dp(sigma), _dp(z), _dp(d), float(K), U,
-                 smap.ctypes.data_as(C.POINTER(C.c_int32)), float(gamma), float(sharing_param), int(c))
+    loc = _LocusV(S, num_snps.ctypes.data, sigma.ctypes.data, z.ctypes.data, d.ctypes.data, float(K), U, smap.ctypes.data,
+                  float(gamma), float(sharing_param), int(c))
     buf = np.zeros(1 + N + S + 3 * U)
     total, post, nc = buf[0:1], buf[1:1 + N], buf[1 + N:1 + N + S]
     sp, sl, nl = buf[1 + N + S:1 + N + S + U], buf[1 + N + S + U:1 + N + S + 2 * U], buf[1 + N + S + 2 * U:]
-    o = _Outputs(_dp(total), _dp(post), _dp(nc), _dp(sp), _dp(sl), _dp(nl))
+    b0 = buf.ctypes.data
+    o = _OutputsV(b0, b0 + 8, b0 + 8 * (1 + N), b0 + 8 * (1 + N + S), b0 + 8 * (1 + N + S + U), b0 + 8 * (1 + N + S + 2 * U))
     cnt = C.c_uint64()
     _check(lib().pipsort_posterior_exhaustive(C.byref(loc), int(device), RAW_LD if raw_ld else 0, int(c), C.byref(o), C.byref(cnt)))
     return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
