@@ -213,7 +213,7 @@ def run_reference_arm(args, L, c, wl):
             "config": {"workload": wl_desc(wl, L, c), "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def wl_desc(wl, L, c):
@@ -223,7 +223,27 @@ def wl_desc(wl, L, c):
 
 
 # ---------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """ONE JSON line on stdout is the contract, but libraries print there too (NCCL's version banner at communicator
+    creation, for instance): point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -256,8 +276,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # keeps NCCL's version banner off stdout: ONE JSON line is the contract
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     # everything (engine kernels, NCCL all-reduce, timing events) is enqueued on ONE non-default stream
@@ -427,7 +445,7 @@ def main():
             line["cpu_baseline"] = cpu
         if sat is not None:
             line["saturating"] = sat
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

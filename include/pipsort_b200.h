@@ -200,15 +200,16 @@ int pipsort_accumulator_buffer(pipsort_engine* e, void** device_ptr, uint64_t* n
 int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copies across devices)  */
 
 /* The same combine step WITHOUT a collective library, over NVLink / NVSwitch peer memory (one process per GPU):
- * every engine exports a mailbox (CUDA IPC handle, PIPSORT_IPC_HANDLE_BYTES bytes), the launcher exchanges the handles
- * (any side channel: torch.distributed all_gather_object, MPI, a file) and hands every rank the whole table.  After that
+ * every engine exports a mailbox (CUDA IPC handle, PIPSORT_IPC_HANDLE_BYTES bytes; one inbox slot per rank of the
+ * group, so the group size is given at export), the launcher exchanges the handles (any side channel:
+ * torch.distributed all_gather_object, MPI, a file) and hands every rank the whole table.  After that
  * pipsort_p2p_reduce_to_root -- stream-ordered, asynchronous, called by EVERY rank after its pipsort_run_exhaustive
- * / scoring calls -- makes the non-root ranks add the non-zero entries of their accumulator stores straight into the
- * root's memory with system-scope fp64 atomics and makes the root wait (on the device) for all of them and fold them
- * into its store: pipsort_read_accumulators on the ROOT then returns the whole job's result.  Engines of one group must
+ * / scoring calls -- makes the non-root ranks copy their accumulator stores straight into their slot of the root's
+ * memory (posted 16-byte stores over the link) and makes the root wait (on the device) for all of them and add them
+ * to its store: pipsort_read_accumulators on the ROOT then returns the whole job's result.  Engines of one group must
  * be created from the same locus and call in lockstep (the n-th call of every rank belongs together).            */
 #define PIPSORT_IPC_HANDLE_BYTES 64
-int pipsort_p2p_export(pipsort_engine* e, void* handle);
+int pipsort_p2p_export(pipsort_engine* e, int world, void* handle);
 int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int rank, int root);
 int pipsort_p2p_reduce_to_root(pipsort_engine* e);
 

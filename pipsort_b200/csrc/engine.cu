@@ -1268,16 +1268,22 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
 static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds);
 
 // ---- peer-memory combine -----------------------------------------------------------------------------------
-int pipsort_p2p_export(pipsort_engine* e, void* handle) {
+// mailbox layout: world slots of slot_len doubles (slot_len = bins_len rounded up to 32 doubles) | 8 control words
+static size_t p2p_slot_len(const pipsort_engine* e) { return (e->bins_len + 31) & ~(size_t)31; }
+
+int pipsort_p2p_export(pipsort_engine* e, int world, void* handle) {
     if (!e || !handle) return fail(PIPSORT_E_ARG, "null argument");
+    if (world < 1 || world > P2P_MAX_WORLD) return fail(PIPSORT_E_ARG, "world=%d outside [1,%d]", world, P2P_MAX_WORLD);
     CU(cudaSetDevice(e->device));
     pipsort_engine::P2P& q = e->p2p;
+    if (q.mailbox && q.world != world) return fail(PIPSORT_E_ARG, "mailbox already exported for world=%d", q.world);
     if (!q.mailbox) {
-        const size_t bytes = (e->bins_len + 8) * sizeof(double);
+        const size_t bytes = ((size_t)world * p2p_slot_len(e) + 8) * sizeof(double);
         CU(cudaMalloc(&q.mailbox, bytes));                       // cudaMalloc (not the pool): CUDA IPC needs it
         CU(cudaMemset(q.mailbox, 0, bytes));
         CU(cudaMalloc(&q.d_done, sizeof(unsigned)));
         CU(cudaMemset(q.d_done, 0, sizeof(unsigned)));
+        q.world = world;
     }
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, q.mailbox));
@@ -1291,11 +1297,12 @@ int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int r
     if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || root < 0 || root >= world)
         return fail(PIPSORT_E_ARG, "bad world/rank/root (%d/%d/%d)", world, rank, root);
     pipsort_engine::P2P& q = e->p2p;
-    if (!q.mailbox) return fail(PIPSORT_E_ARG, "call pipsort_p2p_export first");
+    if (!q.mailbox || q.world != world) return fail(PIPSORT_E_ARG, "call pipsort_p2p_export with the same world first");
     if (q.connected) return fail(PIPSORT_E_ARG, "already connected");
     CU(cudaSetDevice(e->device));
-    q.world = world; q.rank = rank; q.root = root;
+    q.rank = rank; q.root = root;
     q.peers.world = world; q.peers.root = root;
+    const size_t ctrl_off = (size_t)world * p2p_slot_len(e);
     for (int r = 0; r < world; r++) {
         void* base = q.mailbox;
         if (r != rank) {
@@ -1304,7 +1311,7 @@ int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int r
             CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
         }
         q.peer_base[r] = base;
-        q.peers.ctrl[r] = reinterpret_cast<u64*>(static_cast<double*>(base) + e->bins_len);
+        q.peers.ctrl[r] = reinterpret_cast<u64*>(static_cast<double*>(base) + ctrl_off);
     }
     q.epoch = 0;
     q.connected = true;
@@ -1317,14 +1324,14 @@ int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
     if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
     if (q.world == 1) return 0;
     CU(cudaSetDevice(e->device));
-    const size_t n = e->bins_len;
-    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)e->sm_count * 2);
+    const size_t n = e->bins_len, slot = p2p_slot_len(e);
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 511) / 512, (size_t)e->sm_count * 2);
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
     if (q.rank != q.root) {
-        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<double*>(q.peer_base[q.root]), q.peers.ctrl[q.root],
-                                                       q.peers.ctrl[q.rank], q.d_done, errf);
+        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<double*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
+                                                       q.peers.ctrl[q.root], q.peers.ctrl[q.rank], q.d_done, errf);
     } else {
-        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
+        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, slot, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
     }
     e->launches++;
     CU(cudaGetLastError());

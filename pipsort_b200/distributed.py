@@ -5,7 +5,8 @@ The configurations of a locus are independent; the only coupling is the final lo
 * exhaustive (postcal.cpp:716-1092): the union-subset rank space [0, sum_j C(U,j)) is cut into `world`
   contiguous, work-weighted ranges (pipsort_shard_ranks); LD / z / maps are replicated; every rank runs the same
   single launch on its range; the accumulator stores -- plain doubles whose element-wise SUM is the accumulator
-  state of the union, configuration count and error counters included -- are combined by ONE all-reduce(sum).
+  state of the union, configuration count and error counters included -- are combined either by the engine's own
+  peer-memory kernels over NVLink (connect_p2p + collective="p2p") or by ONE all-reduce(sum).
 * stochastic shotgun search (sss_postcal.cpp:223-255): every iteration's list of unseen neighbours is cut into
   `world` contiguous slices, the per-neighbour scores are all-gathered (the sampling step needs all of them on every
   rank, sss_postcal.cpp:289-343), the accumulators stay rank-partial until they are read.
@@ -51,7 +52,7 @@ def connect_p2p(engine, group=None, root=0):
         return False
     ok, mine = True, b""
     try:
-        mine = engine.p2p_export()
+        mine = engine.p2p_export(world)
     except Exception:
         ok = False
     handles = [None] * world

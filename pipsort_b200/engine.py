@@ -96,7 +96,7 @@ def lib():
         L.pipsort_graph_begin.argtypes = [vp]
         L.pipsort_graph_end.argtypes = [vp, C.POINTER(C.c_int32)]
         L.pipsort_graph_launch.argtypes = [vp, C.c_int32]
-        L.pipsort_p2p_export.argtypes = [vp, C.c_char_p]
+        L.pipsort_p2p_export.argtypes = [vp, i32, C.c_char_p]
         L.pipsort_p2p_connect.argtypes = [vp, C.c_char_p, i32, i32, i32]
         L.pipsort_p2p_reduce_to_root.argtypes = [vp]
         L.pipsort_shard_ranks_for_map.argtypes = [C.POINTER(C.c_int32), C.c_int32, i32, i32, C.c_uint32, C.POINTER(u64)]
@@ -326,10 +326,10 @@ class Engine:
     def graph_launch(self, graph_id):
         _check(lib().pipsort_graph_launch(self._h, int(graph_id)))
 
-    def p2p_export(self) -> bytes:
-        """CUDA IPC handle of this engine's mailbox (64 bytes) for the peer-memory combine step."""
+    def p2p_export(self, world) -> bytes:
+        """CUDA IPC handle of this engine's mailbox (64 bytes; one inbox slot per rank of a group of `world`)."""
         buf = C.create_string_buffer(IPC_HANDLE_BYTES)
-        _check(lib().pipsort_p2p_export(self._h, buf))
+        _check(lib().pipsort_p2p_export(self._h, int(world), buf))
         return buf.raw
 
     def p2p_connect(self, handles, rank, root=0):

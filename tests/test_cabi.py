@@ -71,7 +71,7 @@ def test_new_entry_points_reject_bad_arguments_without_touching_cuda():
     assert lib.pipsort_sss_reset(None) == 1
     assert lib.pipsort_score_given_configs(None, None, 0, 0) == 1
     assert lib.pipsort_score_given_configs_device(None, None, 0, 0) == 1
-    assert lib.pipsort_p2p_export(None, None) == 1
+    assert lib.pipsort_p2p_export(None, 2, None) == 1
     assert lib.pipsort_p2p_connect(None, None, 2, 0, 0) == 1
     assert lib.pipsort_p2p_reduce_to_root(None) == 1
     assert lib.pipsort_graph_begin(None) == 1
