@@ -156,11 +156,11 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
                 if (n + already >= (u64)per_slot * slots) return n;
             }
         }
-        if ((n1 + already) * 10 >= slots * 9) { bw = 32; xch = 1; return n1; }
-        for (int w : {16, 8}) {       // small locus: narrower windows only when full ones leave most warps without any item
+        if ((n1 + already) * 2 >= slots) { bw = 32; xch = 1; return n1; }
+        for (int w : {16, 8}) {       // small locus / small shard: narrower windows only when full ones leave most warps idle
             bw = w; xch = 1;          // (150 SNPs/study: 1678 items of (32,1) on 1776 warps beat 3020 items of (16,1))
             n = count_items(bw, xch);
-            if ((n + already) * 10 >= slots * 9) break;
+            if ((n + already) * 2 >= slots) break;
         }
         return n;
     };
