@@ -95,3 +95,30 @@ def test_cli_several_devices_one_process():
             for suf, want in g["files"].items():
                 with open(f"{out}_{suf}.txt") as f:
                     assert f.read() == want, f"{name}: {suf} differs"
+
+
+def test_cli_synthetic_locus_with_psd_iterations_matches_engine():
+    """A 400-SNP/study synthetic locus written in the reference's file formats: the determinant of its LD underflows, so
+    Model's PSD loop really iterates (util.cpp:204-221) -- on the GPU in both paths.  The C++ host (files -> GPU
+    pre-processing -> engine -> six files) must print the numbers the Python path (raw_ld engine) computes."""
+    import numpy as np
+    import pipsort_b200 as P
+    from pipsort_b200 import synth
+    L = synth.make_locus(400, overlap=0.8, seed=77, round_ld=False)
+    with tempfile.TemporaryDirectory() as tmp:
+        ld, z, mp, ns = synth.write_files(L, os.path.join(tmp, "in"))
+        out = os.path.join(tmp, "o")
+        p = subprocess.run([host_bin(), "-l", ld, "-z", z, "-m", mp, "-n", ns, "-o", out, "-c", "2", "-p", "0.5"],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        assert "diagonal shift 0," not in p.stdout                       # the loop added something
+        with P.Engine(L.num_snps, L.sigma, L.z, L.d, 0.0, L.snp_map, gamma=0.01, sharing_param=0.5, max_causal=2,
+                      raw_ld=True) as e:
+            r = e.compute_total_likelihood(2)
+            assert e.prep_info(0)["add_diag"] > 0
+        pips = r.pips()
+        got = [float(line.split("\t")[1]) for line in open(out + "_study0_post.txt").read().splitlines()[1:]]
+        # 6 printed digits; the two runs sum in different orders, and printing rounds to 6 significant digits (5e-6 relative)
+        np.testing.assert_allclose(got, pips[:400], rtol=6e-6, atol=1e-300)
+        nc = [float(x) for x in open(out + "_nocausal.txt").read().split()]
+        np.testing.assert_allclose(nc, r.no_causal(), rtol=6e-6, atol=1e-300)
