@@ -231,7 +231,7 @@ struct pipsort_engine {
     } sss;
     // peer-memory combine (p2p.cuh): this rank's mailbox + the peers' mapped mailboxes
     struct P2P {
-        double* mailbox = nullptr;   // [bins_len] inbox | 8 control words
+        double* mailbox = nullptr;   // world slots (16 bytes per accumulator double) | 8 control words
         unsigned* d_done = nullptr;
         void* peer_base[P2P_MAX_WORLD] = {nullptr};
         P2PPeers peers;
@@ -1268,8 +1268,8 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
 static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds);
 
 // ---- peer-memory combine -----------------------------------------------------------------------------------
-// mailbox layout: world slots of slot_len doubles (slot_len = bins_len rounded up to 32 doubles) | 8 control words
-static size_t p2p_slot_len(const pipsort_engine* e) { return (e->bins_len + 31) & ~(size_t)31; }
+// mailbox layout: world slots of slot_len 16-byte elements (slot_len = bins_len rounded up to 16) | 8 control words
+static size_t p2p_slot_len(const pipsort_engine* e) { return (e->bins_len + 15) & ~(size_t)15; }
 
 int pipsort_p2p_export(pipsort_engine* e, int world, void* handle) {
     if (!e || !handle) return fail(PIPSORT_E_ARG, "null argument");
@@ -1278,7 +1278,7 @@ int pipsort_p2p_export(pipsort_engine* e, int world, void* handle) {
     pipsort_engine::P2P& q = e->p2p;
     if (q.mailbox && q.world != world) return fail(PIPSORT_E_ARG, "mailbox already exported for world=%d", q.world);
     if (!q.mailbox) {
-        const size_t bytes = ((size_t)world * p2p_slot_len(e) + 8) * sizeof(double);
+        const size_t bytes = (size_t)world * p2p_slot_len(e) * sizeof(ulonglong2) + 8 * sizeof(u64);
         CU(cudaMalloc(&q.mailbox, bytes));                       // cudaMalloc (not the pool): CUDA IPC needs it
         CU(cudaMemset(q.mailbox, 0, bytes));
         CU(cudaMalloc(&q.d_done, sizeof(unsigned)));
@@ -1302,7 +1302,7 @@ int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int r
     CU(cudaSetDevice(e->device));
     q.rank = rank; q.root = root;
     q.peers.world = world; q.peers.root = root;
-    const size_t ctrl_off = (size_t)world * p2p_slot_len(e);
+    const size_t ctrl_off = (size_t)world * p2p_slot_len(e) * 2;   // in 8-byte words
     for (int r = 0; r < world; r++) {
         void* base = q.mailbox;
         if (r != rank) {
@@ -1328,10 +1328,11 @@ int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
     const unsigned blocks = (unsigned)std::min<size_t>((n + 511) / 512, (size_t)e->sm_count * 2);
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
     if (q.rank != q.root) {
-        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<double*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
-                                                       q.peers.ctrl[q.root], q.peers.ctrl[q.rank], q.d_done, errf);
+        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<ulonglong2*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
+                                                       q.peers.ctrl[q.rank], q.d_done, errf);
     } else {
-        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, q.mailbox, n, slot, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
+        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, reinterpret_cast<const ulonglong2*>(q.mailbox), n, slot,
+                                                        q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
     }
     e->launches++;
     CU(cudaGetLastError());
