@@ -43,6 +43,9 @@ typedef unsigned long long u64;
 #ifndef EXH_DEFER
 #define EXH_DEFER 1
 #endif
+#ifndef EXH_DEFER_RS
+#define EXH_DEFER_RS 0
+#endif
 constexpr int EXH_WARPS = 4;          // warps per block
 constexpr int EXH_BW = 32;            // max b-window
 constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
@@ -405,6 +408,35 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             double pend[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             int pend_t = -1;
             auto reduce_pending = [&]() {
+#if EXH_DEFER_RS
+                // reduce-scatter of the five sums: 8 double shuffles instead of 25 (each round halves what a lane carries)
+                double q0 = pend[0], q1 = pend[1], q2 = pend[2], q3 = pend[3], q4 = pend[4];
+                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+                {   // xor 16: lower half keeps {q0,q1,q2}, upper half keeps {q3,q4}
+                    const double s0 = h16 ? q0 : q3, s1 = h16 ? q1 : q4, s2 = h16 ? q2 : 0.0;
+                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16),
+                                 r2 = __shfl_xor_sync(0xffffffffu, s2, 16);
+                    q0 = (h16 ? q3 : q0) + r0; q1 = (h16 ? q4 : q1) + r1; q2 = (h16 ? 0.0 : q2) + r2;
+                }
+                {   // xor 8: lower half: sub-half 0 keeps {q0,q1}, sub-half 1 keeps {q2}; upper half: {q0} / {q1}
+                    const double k0 = q0, k1 = h16 ? 0.0 : q1;
+                    const double o0 = h16 ? q1 : q2;
+                    const double s0 = h8 ? k0 : o0, s1 = h8 ? k1 : 0.0;
+                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
+                    q0 = (h8 ? o0 : k0) + r0; q1 = (h8 ? 0.0 : k1) + r1;
+                }
+                {   // xor 4: lanes 0-3 keep X1, lanes 4-7 keep X2; the others just reduce q0
+                    const bool split = lane < 8;
+                    const double s0 = split ? (h4 ? q0 : q1) : q0;
+                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 4);
+                    q0 = (split ? (h4 ? q1 : q0) : q0) + r0;
+                }
+                q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+                q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+                // holders: lane 0 X1, lane 4 X2, lane 8 X3, lane 16 YS, lane 24 YN
+                const int slot = lane == 0 ? X1 : (lane == 4 ? X2 : (lane == 8 ? X3 : (lane == 16 ? YS : (lane == 24 ? YN : -1))));
+                if (slot >= 0) win.acc[pend_t][slot] += q0;
+#else
                 double mine = 0.0;
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
@@ -414,6 +446,7 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     if (lane == k) mine = r;
                 }
                 if (lane < 5) win.acc[pend_t][lane] += mine;
+#endif
             };
             for (int t = 0; t < nb; t++) {
                 const int b = b0 + t;
