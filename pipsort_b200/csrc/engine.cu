@@ -413,6 +413,10 @@ void pipsort_destroy(pipsort_engine* e) {
 
 static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pipsort_engine* e) {
     const int S = lc->num_studies, U = lc->union_count;
+    static const bool trace_create = getenv("PIPSORT_TRACE_CREATE") != nullptr;
+    std::chrono::steady_clock::time_point tr[8];
+    const auto tr_begin = std::chrono::steady_clock::now();
+#define TR(i) do { if (trace_create) tr[i] = std::chrono::steady_clock::now(); } while (0)
     static int ndev = -1;
     if (ndev <= 0 && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) {
         ndev = -1;
@@ -443,6 +447,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->kb = std::min(KMAX, std::max(3, lc->max_causal));
     e->use_reg_kernel = !(flags & PIPSORT_GENERIC_ONLY);
 
+    TR(0);
     // ---- internal order ---------------------------------------------------------------------------
     std::vector<int> type_user(U);
     for (int g = 0; g < U; g++) {
@@ -473,6 +478,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         }
     }
 
+    TR(1);
     // ---- arena: everything dev_alloc hands out below (estimate; the accumulator store is sized for 16 bins) ------------
     {
         size_t est = 64 * 256 + sizeof(LocusDev) + (size_t)(3 + 5 * U + NCOUNTER) * 8 + (size_t)(U + 2) * 8 +
@@ -491,6 +497,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         e->arena_off = 0;
     }
 
+    TR(2);
     // ---- device copy of the locus -------------------------------------------------------------------
     LocusDev& L = e->L;
     memset(&L, 0, sizeof L);
@@ -527,6 +534,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     size_t soff = 0, zoff = 0;
     double maxexp_nats = 0.0, minexp_bits = 0.0;
     double K_total = (flags & PIPSORT_RAW_LD) ? 0.0 : lc->K;
+    TR(3);
     // all host -> device copies of the caller's buffers first, then one event: pipsort_create returns when they are done
     double *up_sigma[2] = {nullptr, nullptr}, *up_z[2] = {nullptr, nullptr};
     bool up_sigma_temp[2] = {false, false};
@@ -547,6 +555,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         }
         CU(cudaEventRecord(e->ev_up, e->stream));
     }
+    TR(4);
     PrepLocusArgs prep_args;
     memset(&prep_args, 0, sizeof prep_args);
     for (int s = 0; s < S; s++) {
@@ -607,6 +616,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             if (up_sigma_temp[s]) CU(cudaFreeAsync(up_sigma[s], e->stream));
     }
 
+    TR(5);
     // ---- prior tables (log_prior, postcal.cpp:19-59) --------------------------------------------------
     const double gam = lc->gamma, p = lc->sharing_param;
     if (!(gam > 0.0 && gam < 1.0)) return fail(PIPSORT_E_ARG, "gamma must be in (0,1)");
@@ -663,6 +673,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         for (int k = 0; k <= KMAX; k++) L.exptab[k] = cache[dslot][k];
     }
 
+    TR(6);
     // ---- accumulator store ------------------------------------------------------------------------------
     const double maxexp_bits = maxexp_nats * 1.4426950408889634 + 128.0;
     minexp_bits += minpi * 1.4426950408889634 - 128.0;
@@ -690,6 +701,12 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->L_host_copy = e->L;
     if ((rc = dev_alloc(e, &e->d_L, 1)) || (rc = upload_small(e, e->d_L, &e->L_host_copy, sizeof(LocusDev)))) return rc;
     if (!e->defer_upload_sync) CU(cudaEventSynchronize(e->ev_up));
+    TR(7);
+    if (trace_create) {
+        auto us = [&](int a, int b) { return std::chrono::duration<double, std::micro>(tr[b] - tr[a]).count(); };
+        fprintf(stderr, "[create] device/kit %.1f | order %.1f | arena %.1f | pack %.1f | uploads %.1f | per-study host %.1f | prep launch+tables %.1f | store+L %.1f us\n",
+                std::chrono::duration<double, std::micro>(tr[0] - tr_begin).count(), us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), us(5, 6), us(6, 7));
+    }
     return 0;
 }
 
@@ -1133,14 +1150,29 @@ int pipsort_last_kernel_ms(pipsort_engine* e, float* ms) {
     return 0;
 }
 
-int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
-    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+// first half of a read: finalize kernel + device -> host copy of the results, enqueued, not waited for
+static int read_enqueue(pipsort_engine* e) {
     int rcf = pipsort_finalize(e);
     if (rcf) return rcf;
-    const int U = e->U;
     if (!e->h_res_pin) e->h_res_pin = reinterpret_cast<double*>(pin_slice(e, e->h_res.size() * sizeof(double)));
     double* hres = e->h_res_pin ? e->h_res_pin : e->h_res.data();
     CU(cudaMemcpyAsync(hres, e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    return 0;
+}
+
+static int read_complete(pipsort_engine* e, const pipsort_outputs* out);
+
+int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    int rcf = read_enqueue(e);
+    if (rcf) return rcf;
+    return read_complete(e, out);
+}
+
+// second half: wait for the engine's stream, check the error counters, scatter into the caller's arrays
+static int read_complete(pipsort_engine* e, const pipsort_outputs* out) {
+    const int U = e->U;
+    double* hres = e->h_res_pin ? e->h_res_pin : e->h_res.data();
     CU(cudaStreamSynchronize(e->stream));
     int rc = flags_to_error(hres + 3 + (size_t)5 * U);
     if (rc) return rc;
@@ -1194,6 +1226,50 @@ int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_
         fprintf(stderr, "[pipsort] create %.1f us, run (enqueue) %.1f us, read (incl. device time) %.1f us, destroy %.1f us\n", us(t0, t1),
                 us(t1, t2), us(t2, t3), us(t3, now()));
     }
+    return rc;
+}
+
+int pipsort_posterior_exhaustive_batch(const pipsort_locus* loci, int32_t n_loci, int device, uint32_t flags, int c,
+                                       const pipsort_outputs* outs, uint64_t* n_configs) {
+    if (n_loci < 0 || (n_loci > 0 && (!loci || !outs))) return fail(PIPSORT_E_ARG, "bad argument");
+    // Software pipeline over DEPTH engines, each on its own stream: while locus i is being evaluated the uploads and the
+    // preparation launches of locus i+1 are already queued, and the results of locus i-DEPTH+1 are being copied back.
+    // Every locus still pays its own host -> device copy, kernels and device -> host read; only the waiting overlaps.
+    constexpr int DEPTH = 3;
+    pipsort_engine* inflight[DEPTH] = {nullptr, nullptr, nullptr};
+    int rc = 0;
+    auto finish = [&](int i) -> int {          // results of locus i (slot i % DEPTH)
+        pipsort_engine*& e = inflight[i % DEPTH];
+        int r = read_complete(e, &outs[i]);
+        if (!r && n_configs) n_configs[i] = e->last_read_count;
+        std::string keep = g_err;
+        pipsort_destroy(e);
+        g_err = keep;
+        e = nullptr;
+        return r;
+    };
+    int i = 0;
+    for (; i < n_loci && !rc; i++) {
+        if (i >= DEPTH) rc = finish(i - DEPTH);
+        if (rc) break;
+        pipsort_engine* e = nullptr;
+        rc = pipsort_create(&loci[i], device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT, &e);
+        if (rc) break;
+        inflight[i % DEPTH] = e;
+        uint64_t total = 0;
+        rc = pipsort_total_ranks(e, c, &total);
+        if (!rc) rc = pipsort_run_exhaustive(e, c, 0, total);
+        if (!rc) rc = read_enqueue(e);
+    }
+    // drain (also after an error: every engine still in flight is destroyed)
+    const int issued = i;
+    for (int j = std::max(0, issued - DEPTH); j < issued; j++) {
+        if (!inflight[j % DEPTH]) continue;
+        if (!rc) rc = finish(j);
+        else { std::string keep = g_err; pipsort_destroy(inflight[j % DEPTH]); g_err = keep; inflight[j % DEPTH] = nullptr; }
+    }
+    for (int d = 0; d < DEPTH; d++)
+        if (inflight[d]) { std::string keep = g_err; pipsort_destroy(inflight[d]); g_err = keep; }
     return rc;
 }
 

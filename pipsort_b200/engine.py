@@ -71,6 +71,8 @@ def lib():
                                                C.POINTER(C.c_double), C.POINTER(_PrepInfo)]
         L.pipsort_prep_info_get.argtypes = [vp, i32, C.POINTER(_PrepInfo)]
         L.pipsort_posterior_exhaustive.argtypes = [C.POINTER(_LocusV), i32, C.c_uint32, i32, C.POINTER(_OutputsV), C.POINTER(u64)]
+        L.pipsort_posterior_exhaustive_batch.argtypes = [C.POINTER(_LocusV), C.c_int32, i32, C.c_uint32, i32,
+                                                         C.POINTER(_OutputsV), C.POINTER(u64)]
         L.pipsort_destroy.argtypes = [vp]
         L.pipsort_destroy.restype = None
         L.pipsort_reset.argtypes = [vp]
@@ -403,6 +405,48 @@ def posterior_exhaustive(num_snps, sigma, z, d, K, snp_map, c, gamma=0.01, shari
     cnt = C.c_uint64()
     _check(lib().pipsort_posterior_exhaustive(C.byref(loc), int(device), RAW_LD if raw_ld else 0, int(c), C.byref(o), C.byref(cnt)))
     return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
+
+
+def posterior_exhaustive_batch(loci, c, device=0, raw_ld=False):
+    """A list of loci in one call (pipsort_posterior_exhaustive_batch): the engine pipelines them over three streams, so
+    the uploads / preparation of the next locus and the read-back of the previous one overlap the current evaluation.
+    loci: sequence of dicts with the keys of posterior_exhaustive's arguments (num_snps, sigma, z, d, K, snp_map and
+    optionally gamma, sharing_param); sigma / z flat float64 arrays (studies concatenated).  Returns a list of Results."""
+    n = len(loci)
+    arr_l = (_LocusV * n)()
+    arr_o = (_OutputsV * n)()
+    keep, views, seen = [], [], {}
+
+    def prepared(a, dtype):        # (contiguous array, address), memoised per input object: loci often share arrays
+        hit = seen.get(id(a))
+        if hit is None:
+            b = np.ascontiguousarray(a, dtype=dtype)
+            hit = seen[id(a)] = (b, b.ctypes.data)
+            keep.append((a, b))
+        return hit
+
+    for i, Lc in enumerate(loci):
+        num_snps, p_ns = prepared(Lc["num_snps"], np.int32)
+        sigma, p_sig = prepared(Lc["sigma"], np.float64)
+        z, p_z = prepared(Lc["z"], np.float64)
+        d, p_d = prepared(Lc["d"], np.float64)
+        smap, p_map = prepared(Lc["snp_map"], np.int32)
+        S, U, N = len(num_snps), int(smap.shape[1]), int(num_snps.sum())
+        buf = np.zeros(1 + N + S + 3 * U)
+        keep.append(buf)
+        arr_l[i] = _LocusV(S, p_ns, p_sig, p_z, p_d, float(Lc["K"]), U, p_map, float(Lc.get("gamma", 0.01)),
+                           float(Lc.get("sharing_param", 0.75)), int(c))
+        b0 = buf.ctypes.data
+        arr_o[i] = _OutputsV(b0, b0 + 8, b0 + 8 * (1 + N), b0 + 8 * (1 + N + S), b0 + 8 * (1 + N + S + U),
+                             b0 + 8 * (1 + N + S + 2 * U))
+        views.append((buf, N, S, U))
+    cnt = (C.c_uint64 * n)()
+    _check(lib().pipsort_posterior_exhaustive_batch(arr_l, n, int(device), RAW_LD if raw_ld else 0, int(c), arr_o, cnt))
+    out = []
+    for i, (buf, N, S, U) in enumerate(views):
+        out.append(Results(float(buf[0]), buf[1:1 + N], buf[1 + N:1 + N + S], buf[1 + N + S:1 + N + S + U],
+                           buf[1 + N + S + U:1 + N + S + 2 * U], buf[1 + N + S + 2 * U:], int(cnt[i])))
+    return out
 
 
 def preprocess_study(ld, z, device=0):

@@ -79,6 +79,9 @@ def test_new_entry_points_reject_bad_arguments_without_touching_cuda():
     assert lib.pipsort_graph_launch(None, 0) == 1
     assert lib.pipsort_prep_info_get(None, 0, None) == 1
     assert lib.pipsort_last_read_config_count(None, ctypes.byref(u64)) == 1
+    assert lib.pipsort_posterior_exhaustive(None, 0, 0, 3, None, None) == 1
+    assert lib.pipsort_posterior_exhaustive_batch(None, 2, 0, 0, 3, None, None) == 1
+    assert lib.pipsort_posterior_exhaustive_batch(None, 0, 0, 0, 3, None, None) == 0
     assert lib.pipsort_preprocess_study(0, -1, None, None, None, None) == 1
     smap = np.zeros((2, 4), dtype=np.int32)
     b = (ctypes.c_uint64 * 3)()

@@ -311,3 +311,24 @@ def test_one_call_posterior_matches_engine_path():
     r = P.posterior_exhaustive(L.n_snps, L.sigma, L.z, L.d, L.K, L.snp_map, 2, gamma=L.gamma, sharing_param=L.p)
     assert r.n_configs == 216817
     assert_results_match(r, g)
+
+
+def test_batch_of_loci_pipelined():
+    """pipsort_posterior_exhaustive_batch: different loci in one call (three engines in flight on three streams); every
+    locus must come back exactly as the one-at-a-time path computes it."""
+    import pipsort_b200 as P
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    loci, want = [], []
+    for i, (n, ov, p) in enumerate([(12, 0.5, 0.75), (40, 0.8, 0.25), (30, 0.0, 0.5), (25, 1.0, 0.75), (60, 0.7, 0.3), (33, 0.8, 0.0),
+                                    (12, 0.5, 0.75)]):
+        SL = synth.make_locus(n, overlap=ov, seed=100 + i, sharing_param=p)
+        loci.append(dict(num_snps=SL.num_snps, sigma=np.concatenate([s.ravel() for s in SL.sigma]), z=np.concatenate(SL.z),
+                         d=SL.d, K=SL.K, snp_map=SL.snp_map, gamma=SL.gamma, sharing_param=p))
+        want.append(O.exhaustive(synth_as_oracle_locus(SL), 3))
+    got = P.posterior_exhaustive_batch(loci, 3)
+    assert len(got) == len(want)
+    for r, w in zip(got, want):
+        assert r.n_configs == w.n_eval
+        assert_results_match(r, w)
+    assert P.posterior_exhaustive_batch([], 3) == []
