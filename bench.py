@@ -397,15 +397,12 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         serial_ms = 1e3 * float(dt.item()) / steps
-        if world > 1:
-            return {"value": total_configs * steps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": serial_ms,
-                    "timing": "host wall clock between device synchronisations, max over ranks (the call includes host work); one "
-                              "locus per call: engine creation (H2D), sharded pass + NCCL all-reduce, read (D2H), destroy"}
-        # One GPU: the call a user with many loci makes -- a LIST of loci in one C-ABI call (pipsort_posterior_exhaustive_batch).
+        # The call a user with many loci makes -- a LIST of loci in one C-ABI call (pipsort_posterior_exhaustive_batch).
         # Every step (= locus) still has its own pinned-host -> device copy of the LD matrices / z / maps, its own kernels
         # and its own device -> host read of the result arrays inside the timed region; the engine overlaps the uploads and
-        # preparation of locus i+1 and the read-back of locus i-1 with the evaluation of locus i (three streams).
+        # preparation of locus i+1 and the read-back of locus i-1 with the evaluation of locus i (three streams).  With
+        # several GPUs the LOCI are dealt out to the ranks (independent units, no collective): every rank runs the same
+        # call on its own list; a single 0.1 ms locus is not worth sharding (single_locus_call_ms shows that path).
         nb = max(steps, 8) * 4
         locus = dict(num_snps=L.num_snps, sigma=sig_np, z=z_np, d=L.d, K=L.K, snp_map=L.snp_map, gamma=L.gamma,
                      sharing_param=L.sharing_param)
@@ -414,14 +411,20 @@ def main():
         t = time.perf_counter()
         rs = P.posterior_exhaustive_batch([locus] * nb, c, device=local)
         barrier()
-        dtb = time.perf_counter() - t
+        dtb = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtb, op=dist.ReduceOp.MAX)
+        dtb = float(dtb.item())
         assert all(x.n_configs == total_configs for x in rs)
         assert abs(rs[-1].total - r.total) <= 1e-9 * abs(r.total)
-        return {"value": total_configs * nb / dtb, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dtb / nb, "loci_per_call": nb, "single_locus_call_ms": serial_ms,
-                "timing": "host wall clock around ONE call that evaluates loci_per_call loci from pinned host buffers (per locus: "
-                          "H2D of LD / z / maps, preparation + exhaustive + finalize kernels, D2H of the result arrays; three "
-                          "loci in flight on three streams); single_locus_call_ms = the same work as one call per locus"}
+        return {"value": total_configs * nb * world / dtb, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * dtb / (nb * world), "loci_per_call": nb, "loci_total": nb * world,
+                "single_locus_call_ms": serial_ms,
+                "timing": "host wall clock (max over ranks) around ONE call per rank that evaluates loci_per_call loci from pinned "
+                          "host buffers (per locus: H2D of LD / z / maps, preparation + exhaustive + finalize kernels, D2H of the "
+                          "result arrays; three loci in flight on three streams per GPU; loci dealt out to the ranks, no "
+                          "collective); single_locus_call_ms = one locus per call"
+                          + (" with its rank space sharded over the GPUs and one NCCL all-reduce" if world > 1 else "")}
 
     peak = P.measure_fp64_peak(local)                      # FLOP/s, DFMA chains on every SM
     main_m = measure(L, c, args.steps, args.warmup, clocks=True)
