@@ -535,7 +535,6 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
                     accX[YS] += sumY(g[2]);
                     accX[YN] += sumY(g[0]) + sumY(g[1]);
-                    accT += (x1 + x2) + x3;                                        // every expansion exactly once
                 }
                 if (HAS_A) {   // a cells -> lane registers (flushed at the end of the item)
                     double g[3][3];
@@ -573,7 +572,6 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
                     accX[YS] += sumY(G[2][2]);
                     accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
-                    accT += (x1 + x2) + x3;
                 }
                 if (HAS_A) {
                     accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
@@ -646,6 +644,7 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             if (pend_t >= 0) reduce_pending();
 #endif
 
+            accT += (accX[X1] + accX[X2]) + accX[X3];   // every expansion is in exactly one x cell: the total, once per tile
             if (xin) {   // flush the x cells of this tile
 #pragma unroll
                 for (int k = 0; k < 5; k++) bin_add(acc, k, x, accX[k], 0);
