@@ -46,7 +46,10 @@ typedef unsigned long long u64;
 #ifndef EXH_DEFER_RS
 #define EXH_DEFER_RS 0
 #endif
-constexpr int EXH_WARPS = 4;          // warps per block
+#ifndef EXH_WARPS_PER_BLOCK
+#define EXH_WARPS_PER_BLOCK 4
+#endif
+constexpr int EXH_WARPS = EXH_WARPS_PER_BLOCK;   // warps per block
 constexpr int EXH_BW = 32;            // max b-window
 constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
 constexpr double FAST_LIMIT = 0x1p+450;
