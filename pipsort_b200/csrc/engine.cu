@@ -125,6 +125,22 @@ __device__ inline XAcc bins_read_warp(const AccDev& a, int slot, int g, int lane
     return XAcc{M, 512 * top - a.bias + e};
 }
 
+// The same from registers when the accumulator has at most 32 bins: lane b holds bin b (all the loads of a SNP's five
+// accumulators are then issued together -- one memory round trip instead of ten dependent ones).
+__device__ inline XAcc bins_from_lanes(double v, int bias) {
+    const unsigned mask = __ballot_sync(0xffffffffu, v > 0.0);
+    if (!mask) return xacc_empty();
+    const int top = 31 - __clz(mask);
+    double M = __shfl_sync(0xffffffffu, v, top);
+    const double m1 = __shfl_sync(0xffffffffu, v, max(top - 1, 0)), m2 = __shfl_sync(0xffffffffu, v, max(top - 2, 0));
+    if (top > 0) M += m1 * 0x1p-512;
+    if (top > 1) M += (m2 * 0x1p-512) * 0x1p-512;
+    const int hi = __double2hiint(M);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    M = __hiloint2double(hi - (e << 20), __double2loint(M));
+    return XAcc{M, 512 * top - bias + e};
+}
+
 // log(M 2^N) + c ; 0.0 (the reference's "empty" sentinel, postcal.h:102-112) when nothing was added
 __device__ inline double xlog_or_zero(const XAcc& a, double c) {
     if (!(a.M > 0.0)) return 0.0;
@@ -148,18 +164,24 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, in
     }
     const int g = w - 3;
     if (g >= U) return;
-    const XAcc x1 = bins_read_warp(acc, X1, g, lane), x2 = bins_read_warp(acc, X2, g, lane), x3 = bins_read_warp(acc, X3, g, lane);
-    const XAcc ys = bins_read_warp(acc, YS, g, lane), yn = bins_read_warp(acc, YN, g, lane);
-    if (lane != 0) return;
+    XAcc x1, x2, x3, ys, yn;
+    if (acc.NB <= 32) {
+        double v[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[k] = lane < acc.NB ? bin_ptr(acc, k, g)[(size_t)lane * acc.Upad] : 0.0;   // X1 X2 X3 YS YN
+        x1 = bins_from_lanes(v[X1], acc.bias); x2 = bins_from_lanes(v[X2], acc.bias); x3 = bins_from_lanes(v[X3], acc.bias);
+        ys = bins_from_lanes(v[YS], acc.bias); yn = bins_from_lanes(v[YN], acc.bias);
+    } else {
+        x1 = bins_read_warp(acc, X1, g, lane); x2 = bins_read_warp(acc, X2, g, lane); x3 = bins_read_warp(acc, X3, g, lane);
+        ys = bins_read_warp(acc, YS, g, lane); yn = bins_read_warp(acc, YN, g, lane);
+    }
+    if (lane >= 5) return;
     XAcc p0 = x1, p1 = x2;
     xmerge(p0, x3);
     xmerge(p1, x3);
-    double* r = res + 3;
-    r[g] = xlog_or_zero(p0, cx);
-    r[U + g] = xlog_or_zero(p1, cx);
-    r[2 * U + g] = xlog_or_zero(x3, cx);
-    r[3 * U + g] = xlog_or_zero(ys, cy);
-    r[4 * U + g] = xlog_or_zero(yn, cy);
+    // five logarithms: one lane each
+    const XAcc mine = lane == 0 ? p0 : (lane == 1 ? p1 : (lane == 2 ? x3 : (lane == 3 ? ys : yn)));
+    res[3 + (size_t)lane * U + g] = xlog_or_zero(mine, lane < 3 ? cx : cy);
 }
 
 __global__ void add_bins_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
