@@ -332,3 +332,42 @@ def test_batch_of_loci_pipelined():
         assert r.n_configs == w.n_eval
         assert_results_match(r, w)
     assert P.posterior_exhaustive_batch([], 3) == []
+
+
+def test_edge_cases_empty_and_ragged():
+    """Empty union, a study without SNPs, a single SNP, c larger than U: the counts and sums of the oracle."""
+    import pipsort_b200 as P
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    # no SNP at all: only the null configuration exists (postcal.cpp:793-822)
+    with P.Engine([0, 0], np.zeros(0), np.zeros(0), [5.72, 5.72], 3.0, np.zeros((2, 0), dtype=np.int32), max_causal=3) as e:
+        r = e.compute_total_likelihood(3)
+        assert r.n_configs == 1 and r.total == pytest.approx(-3.0 / 2 - 1.0, rel=1e-14)
+        assert r.noCausal.tolist() == [r.total, r.total]
+    # ragged: study 1 has no SNP, study 0 has four; c = 3 > number of shared SNPs (0)
+    SL = synth.make_locus(4, overlap=0.0, seed=9)
+    smap = np.array([[0, 1, 2, 3], [-1, -1, -1, -1]], dtype=np.int32)
+    L = O.Locus(n_snps=np.array([4, 0], dtype=np.int32), sigma=[SL.sigma[0], np.zeros((0, 0))], z=[SL.z[0], np.zeros(0)], K=1.25,
+                d=SL.d, snp_map=smap, gamma=0.01, p=0.75)
+    want = O.exhaustive(L, 3)
+    with engine_for(L, 3) as e:
+        r = e.compute_total_likelihood(3)
+    assert r.n_configs == want.n_eval == 1 + 4 + 6 + 4
+    assert_results_match(r, want)
+    # one shared SNP, c = 3 > U = 1
+    L1 = O.Locus(n_snps=np.array([1, 1], dtype=np.int32), sigma=[np.ones((1, 1)), np.ones((1, 1))], z=[np.array([2.5]), np.array([-1.0])],
+                 K=7.25, d=np.array([5.72, 5.72]), snp_map=np.zeros((2, 1), dtype=np.int32), gamma=0.01, p=0.75)
+    want = O.exhaustive(L1, 3)
+    with engine_for(L1, 3) as e:
+        r = e.compute_total_likelihood(3)
+    assert r.n_configs == want.n_eval == 4
+    assert_results_match(r, want)
+
+
+def test_out_of_range_locus_is_refused():
+    """z-scores so large that exp(f) leaves every representable range: PIPSORT_E_RANGE at create, not garbage later."""
+    import pipsort_b200 as P
+    with pytest.raises(P.PipsortError) as ei:
+        P.Engine([1, 1], [np.ones((1, 1)), np.ones((1, 1))], [np.array([1e6]), np.array([1.0])], [257.0, 5.72], 1.0,
+                 np.zeros((2, 1), dtype=np.int32), max_causal=3)
+    assert ei.value.code == 4
