@@ -46,6 +46,9 @@ typedef unsigned long long u64;
 #ifndef EXH_DEFER_RS
 #define EXH_DEFER_RS 0
 #endif
+#ifndef EXH_SMEM_ACC
+#define EXH_SMEM_ACC 0     // item-lifetime accumulators (a cells, noCausal) in shared memory instead of registers
+#endif
 #ifndef EXH_WARPS_PER_BLOCK
 #define EXH_WARPS_PER_BLOCK 4
 #endif
@@ -260,6 +263,9 @@ struct WinStudy {
 struct WarpWin {
     WinStudy st[2];
     double acc[EXH_BW][5];   // b-cell accumulators of the window, flushed at the end of the item
+#if EXH_SMEM_ACC
+    double item[7][32];      // per-lane item-lifetime sums: a cells X1 X2 X3 YS YN, noCausal[0], noCausal[1]
+#endif
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
 
@@ -358,7 +364,19 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
         __syncwarp();
 
         // ---- item-lifetime accumulators (lane private, plain doubles) ------------------------------------------
+#if EXH_SMEM_ACC
+        double accT = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) win.item[k][lane] = 0.0;
+#define ACC_A(k) win.item[k][lane]
+#define ACC_NC0 win.item[5][lane]
+#define ACC_NC1 win.item[6][lane]
+#else
         double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+#define ACC_A(k) accA[k]
+#define ACC_NC0 accNC0
+#define ACC_NC1 accNC1
+#endif
         unsigned nconf = 0;
 
         for (int xt = xt0; xt < xt0 + nxt; xt++) {
@@ -542,13 +560,13 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 if (HAS_A) {   // a cells -> lane registers (flushed at the end of the item)
                     double g[3][3];
                     cell(0, g);
-                    accA[X1] += wsumX(g[0], false); accA[X2] += wsumX(g[1], false); accA[X3] += wsumX(g[2], true);
-                    accA[YS] += sumY(g[2]);
-                    accA[YN] += sumY(g[0]) + sumY(g[1]);
+                    ACC_A(X1) += wsumX(g[0], false); ACC_A(X2) += wsumX(g[1], false); ACC_A(X3) += wsumX(g[2], true);
+                    ACC_A(YS) += sumY(g[2]);
+                    ACC_A(YN) += sumY(g[0]) + sumY(g[1]);
                 }
                 // no causal SNP in study 1 (0): every chosen SNP causal in study 0 (1) only  (postcal.cpp:988-1000)
-                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
-                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+                ACC_NC1 = fma(pi0, v[0][HAS_A ? 7 : 6], ACC_NC1);
+                ACC_NC0 = fma(pi0, v[1][HAS_A ? 7 : 6], ACC_NC0);
 #else
                 double G[3][3][3];
 #pragma unroll
@@ -577,12 +595,12 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
                 }
                 if (HAS_A) {
-                    accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
-                    accA[YS] += sumY(G[0][2]);
-                    accA[YN] += sumY(G[0][0]) + sumY(G[0][1]);
+                    ACC_A(X1) += wsumX(G[0][0], false); ACC_A(X2) += wsumX(G[0][1], false); ACC_A(X3) += wsumX(G[0][2], true);
+                    ACC_A(YS) += sumY(G[0][2]);
+                    ACC_A(YN) += sumY(G[0][0]) + sumY(G[0][1]);
                 }
-                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
-                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+                ACC_NC1 = fma(pi0, v[0][HAS_A ? 7 : 6], ACC_NC1);
+                ACC_NC0 = fma(pi0, v[1][HAS_A ? 7 : 6], ACC_NC0);
 #endif
                 {   // b cells -> reduce-scatter over the warp (8 shuffles) -> shared-memory window accumulators
 #if EXH_CELLMAJOR
@@ -663,8 +681,11 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
         {
             double r[8];
 #pragma unroll
-            for (int k = 0; k < 5; k++) r[k] = accA[k];
-            r[5] = accT; r[6] = accNC0; r[7] = accNC1;
+            for (int k = 0; k < 5; k++) r[k] = ACC_A(k);
+            r[5] = accT; r[6] = ACC_NC0; r[7] = ACC_NC1;
+#undef ACC_A
+#undef ACC_NC0
+#undef ACC_NC1
             unsigned cnt = nconf;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
