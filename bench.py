@@ -74,7 +74,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.idx)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -340,7 +340,18 @@ def main():
             kms.append(None)
         barrier()
         t_wall = time.perf_counter() - t_wall
+        if clocks:
+            # the timed region lasts a few milliseconds (20 steps of 0.07 ms): keep the SAME step running back to back for
+            # another ~0.3 s, untimed, so that nvidia-smi (20 ms period) sees the clocks / throttle reasons under this load
+            t_load = time.perf_counter()
+            while time.perf_counter() - t_load < 0.3:
+                for _ in range(50):
+                    run()
+                e.sync()
+            barrier()
         clk = sampler.stop() if clocks and rank == 0 else None
+        if clk is not None:
+            clk["window"] = "timed region + 0.3 s of the same step repeated back to back (untimed), nvidia-smi every 20 ms"
         launches = launches_per_step * steps
         ms = [a.elapsed_time(z) for a, z in evs]
         if os.environ.get("PIPSORT_BENCH_DEBUG"):
