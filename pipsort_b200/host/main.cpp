@@ -29,7 +29,8 @@ int pipsort_main(int argc, char* argv[]) {
             case 'l': ldFile = optarg; break;
             case 'o': outputFileName = optarg; break;
             case 'z': zFile = optarg; break;
-            case 'm': snpMapFile = optarg;       // falls through, pipsort.cpp:128-132
+            case 'm': snpMapFile = optarg;       // falls through on purpose: pipsort.cpp:128-132 has no break here
+                [[fallthrough]];
             case 'n': sample_s = optarg; break;
             case 'b': configsFile = optarg; break;
             case 'd': num_configs = std::atoi(optarg); break;
