@@ -217,6 +217,21 @@ def exhaustive_omp(L: Locus, c: int, rank_begin: int, rank_end: int, threads: in
     return tot.value, int(ne.value)
 
 
+def exhaustive_omp_full(L: Locus, c: int, rank_begin: int = 0, rank_end: int | None = None, threads: int = 0) -> Result:
+    """exhaustive() on all host cores (per-thread accumulators merged in log space): every accumulator, for the sizes the
+    sequential walk would take minutes on (12 M configurations of the 150-SNP c=3 locus, rank ranges of the 1500-SNP one)."""
+    n, sig, z, d, smap = L.flat()
+    if rank_end is None:
+        rank_end = total_union_subsets(L.U, c)
+    post = np.zeros(L.N); nc = np.zeros(L.S); sp = np.zeros(L.U); sl = np.zeros(L.U); nl = np.zeros(L.U)
+    tot = C.c_double(); ne = _u64()
+    rc = lib().oracle_exhaustive_omp_full(L.S, _i(n), _d(sig), _d(z), C.c_double(L.K), _d(d), L.U, _i(smap), int(c),
+                                          C.c_double(L.gamma), C.c_double(L.p), _u64(rank_begin), _u64(rank_end),
+                                          int(threads), C.byref(tot), _d(post), _d(nc), _d(sp), _d(sl), _d(nl), C.byref(ne))
+    assert rc == 0
+    return Result(tot.value, post, nc, sp, sl, nl, int(ne.value))
+
+
 def score_union_configs(L: Locus, idx: np.ndarray, make_updates=None, state: Result | None = None):
     """sss_postcal.cpp:447-685 for a batch; returns (max_abs_l[n], Result with updated accumulators)."""
     n, sig, z, d, smap = L.flat()

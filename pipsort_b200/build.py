@@ -1,6 +1,7 @@
 """Builds the engine in-tree: pipsort_b200/lib/libpipsort_b200.so (nvcc, sm_100a only)."""
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -19,11 +20,30 @@ def _nvcc():
     return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 
 
-def _stale(target, sources):
+def _digest(sources, extra=""):
+    """Content hash of the sources (mtimes do not survive a snapshot copy to the GPU box; contents do)."""
+    h = hashlib.sha256(extra.encode())
+    for s in sorted(sources):
+        h.update(os.path.basename(s).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target, sources, extra=""):
+    """True when `target` is missing or was built from other sources (hash recorded next to it at build time)."""
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    try:
+        with open(target + ".srchash") as f:
+            return f.read().strip() != _digest(sources, extra)
+    except OSError:
+        return True
+
+
+def _stamp(target, sources, extra=""):
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(sources, extra))
 
 
 def sources():
@@ -34,9 +54,12 @@ def sources():
 
 def build_engine(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
-    if force or _stale(LIB, sources()):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "engine.cu"), "-o", LIB]
+    flags = " ".join(NVCC_FLAGS)
+    if force or _stale(LIB, sources(), flags):
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "engine.cu"), "-o", LIB + ".tmp"]
         subprocess.check_call(cmd)
+        os.replace(LIB + ".tmp", LIB)          # atomic: several ranks may load the library while one rebuilds it
+        _stamp(LIB, sources(), flags)
     return LIB
 
 
@@ -46,11 +69,13 @@ def build_host(force: bool = False) -> str | None:
     if not os.path.isdir(hdir):
         return None
     srcs = [os.path.join(hdir, f) for f in sorted(os.listdir(hdir)) if f.endswith(".cpp")]
-    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB]
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + \
+        [os.path.join(os.path.dirname(PKG), "include", "pipsort_b200.h")]
     if srcs and (force or _stale(HOST_BIN, deps)):
         cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(os.path.dirname(PKG), "include")] + srcs + \
               ["-o", HOST_BIN, "-L", LIBDIR, "-lpipsort_b200", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
+        _stamp(HOST_BIN, deps)
     return HOST_BIN if srcs else None
 
 

@@ -298,8 +298,13 @@ void kit_release(int device, const StreamKit& k) {
     kit_cache(device).push_back(k);
 }
 
+// one-time, per-process initialisations (device count, SM counts, pool thresholds, expansion tables, occupancy) may be
+// reached by several host threads creating their first engines at once: they all run under this mutex
+std::mutex& init_mutex() { static std::mutex m; return m; }
+
 int pool_setup(int device) {
     static bool done[64] = {false};
+    std::lock_guard<std::mutex> g(init_mutex());
     if (device < 64 && done[device]) return 0;
     cudaMemPool_t pool;
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -439,16 +444,22 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     std::chrono::steady_clock::time_point tr[8];
     const auto tr_begin = std::chrono::steady_clock::now();
 #define TR(i) do { if (trace_create) tr[i] = std::chrono::steady_clock::now(); } while (0)
-    static int ndev = -1;
-    if (ndev <= 0 && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) {
-        ndev = -1;
-        return fail(PIPSORT_E_CUDA, "no CUDA device available (the engine has no CPU path)");
+    int ndev_now;
+    {
+        static int ndev = -1;
+        std::lock_guard<std::mutex> g(init_mutex());
+        if (ndev <= 0 && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)) {
+            ndev = -1;
+            return fail(PIPSORT_E_CUDA, "no CUDA device available (the engine has no CPU path)");
+        }
+        ndev_now = ndev;
     }
-    if (device < 0 || device >= ndev) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev);
+    if (device < 0 || device >= ndev_now) return fail(PIPSORT_E_ARG, "device %d out of range (have %d)", device, ndev_now);
     CU(cudaSetDevice(device));
     e->device = device;
     {
         static int sm_cache[64] = {0};
+        std::lock_guard<std::mutex> g(init_mutex());
         if (!sm_cache[device & 63]) CU(cudaDeviceGetAttribute(&sm_cache[device & 63], cudaDevAttrMultiProcessorCount, device));
         e->sm_count = sm_cache[device & 63];
     }
@@ -668,6 +679,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     {
         static uint32_t* cache[64][KMAX + 1] = {{nullptr}};
         const int dslot = device & 63;
+        std::lock_guard<std::mutex> g(init_mutex());      // all KMAX + 1 pointers are published under the lock
         if (!cache[dslot][0]) {
             size_t total = 0;
             int n3s[KMAX + 1];
@@ -917,6 +929,9 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     return 0;
 }
 
+static int check_flags(pipsort_engine* e);
+static int flags_to_error(const double* counters);
+
 int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
                                        const uint8_t* d_make_updates, double* d_out) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
@@ -950,8 +965,7 @@ int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n
     int rc = pipsort_score_union_configs_device(e, e->d_idx, n, kmax, make_updates ? e->d_upd : nullptr, e->d_out);
     if (rc) return rc;
     if (out_max_abs_l) CU(cudaMemcpyAsync(out_max_abs_l, e->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    return 0;
+    return check_flags(e);      // one synchronisation: the values and the error counters (a refused row, a singular block)
 }
 
 int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_configs, int64_t num_configs, int num_groups) {
@@ -967,9 +981,6 @@ int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_confi
     CU(cudaGetLastError());
     return 0;
 }
-
-static int check_flags(pipsort_engine* e);
-static int flags_to_error(const double* counters);
 
 // ---- stochastic shotgun search -----------------------------------------------------------------------------
 static int sss_table_alloc(SssTable* t, u64 cap, cudaStream_t st) {

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "exhaustive_dev.cuh"
@@ -97,6 +98,8 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     if (!sc->d_counter && (err = cudaMallocAsync(&sc->d_counter, sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
     if (!sc->occ) {
         static int occ_cache = 0;    // a property of the kernel and the device generation: query once per process
+        static std::mutex occ_mutex;
+        std::lock_guard<std::mutex> g(occ_mutex);
         if (!occ_cache && (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
         sc->occ = occ_cache;
     }

@@ -31,24 +31,6 @@ typedef unsigned long long u64;
 #ifndef EXH_MINBLOCKS
 #define EXH_MINBLOCKS 3
 #endif
-#ifndef EXH_PREFETCH
-#define EXH_PREFETCH 1
-#endif
-#ifndef EXH_CELLMAJOR
-#define EXH_CELLMAJOR 0
-#endif
-#ifndef EXH_RSCATTER
-#define EXH_RSCATTER 0
-#endif
-#ifndef EXH_DEFER
-#define EXH_DEFER 1
-#endif
-#ifndef EXH_DEFER_RS
-#define EXH_DEFER_RS 0
-#endif
-#ifndef EXH_SMEM_ACC
-#define EXH_SMEM_ACC 0     // item-lifetime accumulators (a cells, noCausal) in shared memory instead of registers
-#endif
 #ifndef EXH_WARPS_PER_BLOCK
 #define EXH_WARPS_PER_BLOCK 4
 #endif
@@ -263,9 +245,6 @@ struct WinStudy {
 struct WarpWin {
     WinStudy st[2];
     double acc[EXH_BW][5];   // b-cell accumulators of the window, flushed at the end of the item
-#if EXH_SMEM_ACC
-    double item[7][32];      // per-lane item-lifetime sums: a cells X1 X2 X3 YS YN, noCausal[0], noCausal[1]
-#endif
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
 
@@ -364,19 +343,7 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
         __syncwarp();
 
         // ---- item-lifetime accumulators (lane private, plain doubles) ------------------------------------------
-#if EXH_SMEM_ACC
-        double accT = 0.0;
-#pragma unroll
-        for (int k = 0; k < 7; k++) win.item[k][lane] = 0.0;
-#define ACC_A(k) win.item[k][lane]
-#define ACC_NC0 win.item[5][lane]
-#define ACC_NC1 win.item[6][lane]
-#else
         double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
-#define ACC_A(k) accA[k]
-#define ACC_NC0 accNC0
-#define ACC_NC1 accNC1
-#endif
         unsigned nconf = 0;
 
         for (int xt = xt0; xt < xt0 + nxt; xt++) {
@@ -429,35 +396,6 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             double pend[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             int pend_t = -1;
             auto reduce_pending = [&]() {
-#if EXH_DEFER_RS
-                // reduce-scatter of the five sums: 8 double shuffles instead of 25 (each round halves what a lane carries)
-                double q0 = pend[0], q1 = pend[1], q2 = pend[2], q3 = pend[3], q4 = pend[4];
-                const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-                {   // xor 16: lower half keeps {q0,q1,q2}, upper half keeps {q3,q4}
-                    const double s0 = h16 ? q0 : q3, s1 = h16 ? q1 : q4, s2 = h16 ? q2 : 0.0;
-                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16),
-                                 r2 = __shfl_xor_sync(0xffffffffu, s2, 16);
-                    q0 = (h16 ? q3 : q0) + r0; q1 = (h16 ? q4 : q1) + r1; q2 = (h16 ? 0.0 : q2) + r2;
-                }
-                {   // xor 8: lower half: sub-half 0 keeps {q0,q1}, sub-half 1 keeps {q2}; upper half: {q0} / {q1}
-                    const double k0 = q0, k1 = h16 ? 0.0 : q1;
-                    const double o0 = h16 ? q1 : q2;
-                    const double s0 = h8 ? k0 : o0, s1 = h8 ? k1 : 0.0;
-                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
-                    q0 = (h8 ? o0 : k0) + r0; q1 = (h8 ? 0.0 : k1) + r1;
-                }
-                {   // xor 4: lanes 0-3 keep X1, lanes 4-7 keep X2; the others just reduce q0
-                    const bool split = lane < 8;
-                    const double s0 = split ? (h4 ? q0 : q1) : q0;
-                    const double r0 = __shfl_xor_sync(0xffffffffu, s0, 4);
-                    q0 = (split ? (h4 ? q1 : q0) : q0) + r0;
-                }
-                q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
-                q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
-                // holders: lane 0 X1, lane 4 X2, lane 8 X3, lane 16 YS, lane 24 YN
-                const int slot = lane == 0 ? X1 : (lane == 4 ? X2 : (lane == 8 ? X3 : (lane == 16 ? YS : (lane == 24 ? YN : -1))));
-                if (slot >= 0) win.acc[pend_t][slot] += q0;
-#else
                 double mine = 0.0;
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
@@ -467,14 +405,11 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     if (lane == k) mine = r;
                 }
                 if (lane < 5) win.acc[pend_t][lane] += mine;
-#endif
             };
             for (int t = 0; t < nb; t++) {
                 const int b = b0 + t;
                 if (b >= xt * 32 + 31) break;                       // no x of this tile is beyond b
-#if EXH_DEFER
                 if (pend_t >= 0) reduce_pending();
-#endif
                 bool active = xin;
                 if (diag) {
                     active = active && x > b;
@@ -525,49 +460,11 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 }
 
                 // ---- cells: g[state][a'] = sum over the expansions with one SNP in that state, a' = number of
-                // OTHER SNPs causal in both studies.  One SNP at a time (9 live sums instead of 27).
+                // OTHER SNPs causal in both studies.
                 auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
                     return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
                 };
                 auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
-                auto cell = [&](const int I, double (&g)[3][3]) {   // I: 0 = a, 1 = b, 2 = x
-#pragma unroll
-                    for (int q = 0; q < 3; q++)
-#pragma unroll
-                        for (int r = 0; r < 3; r++) g[q][r] = 0.0;
-#pragma unroll
-                    for (int tx = 0; tx < 3; tx++)
-#pragma unroll
-                        for (int tb = 0; tb < 3; tb++)
-#pragma unroll
-                            for (int ta = 0; ta < (HAS_A ? 3 : 1); ta++) {
-                                const int m0 = (HAS_A && in0(ta) ? 1 : 0) | (in0(tb) ? 2 : 0) | (in0(tx) ? 4 : 0);
-                                const int m1 = (HAS_A && in1(ta) ? 1 : 0) | (in1(tb) ? 2 : 0) | (in1(tx) ? 4 : 0);
-                                const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
-                                const int ti = I == 0 ? ta : (I == 1 ? tb : tx);
-                                g[ti][ac - (ti == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], g[ti][ac - (ti == 2 ? 1 : 0)]);
-                            }
-                };
-#if EXH_CELLMAJOR
-                {   // x cells -> lane registers (flushed after the window)
-                    double g[3][3];
-                    cell(2, g);
-                    const double x1 = wsumX(g[0], false), x2 = wsumX(g[1], false), x3 = wsumX(g[2], true);
-                    accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
-                    accX[YS] += sumY(g[2]);
-                    accX[YN] += sumY(g[0]) + sumY(g[1]);
-                }
-                if (HAS_A) {   // a cells -> lane registers (flushed at the end of the item)
-                    double g[3][3];
-                    cell(0, g);
-                    ACC_A(X1) += wsumX(g[0], false); ACC_A(X2) += wsumX(g[1], false); ACC_A(X3) += wsumX(g[2], true);
-                    ACC_A(YS) += sumY(g[2]);
-                    ACC_A(YN) += sumY(g[0]) + sumY(g[1]);
-                }
-                // no causal SNP in study 1 (0): every chosen SNP causal in study 0 (1) only  (postcal.cpp:988-1000)
-                ACC_NC1 = fma(pi0, v[0][HAS_A ? 7 : 6], ACC_NC1);
-                ACC_NC0 = fma(pi0, v[1][HAS_A ? 7 : 6], ACC_NC0);
-#else
                 double G[3][3][3];
 #pragma unroll
                 for (int i = 0; i < 3; i++)
@@ -595,75 +492,21 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                     accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
                 }
                 if (HAS_A) {
-                    ACC_A(X1) += wsumX(G[0][0], false); ACC_A(X2) += wsumX(G[0][1], false); ACC_A(X3) += wsumX(G[0][2], true);
-                    ACC_A(YS) += sumY(G[0][2]);
-                    ACC_A(YN) += sumY(G[0][0]) + sumY(G[0][1]);
+                    accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
+                    accA[YS] += sumY(G[0][2]);
+                    accA[YN] += sumY(G[0][0]) + sumY(G[0][1]);
                 }
-                ACC_NC1 = fma(pi0, v[0][HAS_A ? 7 : 6], ACC_NC1);
-                ACC_NC0 = fma(pi0, v[1][HAS_A ? 7 : 6], ACC_NC0);
-#endif
-                {   // b cells -> reduce-scatter over the warp (8 shuffles) -> shared-memory window accumulators
-#if EXH_CELLMAJOR
-                    double g[3][3];
-                    cell(1, g);
-#else
+                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
+                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+                {   // b cells: warp-reduced one step later (reduce_pending) into the shared-memory window accumulators
                     double (&g)[3][3] = G[1];
-#endif
                     double q0 = wsumX(g[0], false), q1 = wsumX(g[1], false), q2 = wsumX(g[2], true);   // X1 X2 X3
                     double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
-#if EXH_DEFER
                     pend[0] = q0; pend[1] = q1; pend[2] = q2; pend[3] = q3; pend[4] = q4;
                     pend_t = t;
-#elif !EXH_RSCATTER
-                    {
-                        double vb[5] = {q0, q1, q2, q3, q4};
-                        double mine = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 5; k++) {
-                            double r = vb[k];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                            if (lane == k) mine = r;
-                        }
-                        if (lane < 5) win.acc[t][lane] += mine;
-                    }
-#else
-                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-                    // round 1 (xor 16): lower half keeps {q0,q1,q2}, upper half keeps {q3,q4}
-                    {
-                        const double s0 = h16 ? q0 : q3, s1 = h16 ? q1 : q4, s2 = h16 ? q2 : 0.0;
-                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16),
-                                     r2 = __shfl_xor_sync(0xffffffffu, s2, 16);
-                        q0 = (h16 ? q3 : q0) + r0; q1 = (h16 ? q4 : q1) + r1; q2 = (h16 ? 0.0 : q2) + r2;
-                    }
-                    // now lower half: (q0,q1,q2) = partial (X1,X2,X3); upper half: (q0,q1) = partial (YS,YN), q2 = 0
-                    // round 2 (xor 8): sub-half 0 keeps {q0,q1}, sub-half 1 keeps {q2}  (upper half: {q0} / {q1})
-                    {
-                        const double k0 = h16 ? q0 : q0, k1 = h16 ? 0.0 : q1;          // what sub-half 0 keeps
-                        const double o0 = h16 ? q1 : q2;                                // what sub-half 1 keeps
-                        const double s0 = h8 ? k0 : o0, s1 = h8 ? k1 : 0.0;
-                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 8), r1 = __shfl_xor_sync(0xffffffffu, s1, 8);
-                        q0 = (h8 ? o0 : k0) + r0; q1 = (h8 ? 0.0 : k1) + r1;
-                    }
-                    // lanes 0-7: (q0,q1) = (X1,X2); 8-15: q0 = X3; 16-23: q0 = YS; 24-31: q0 = YN
-                    // round 3 (xor 4): lanes 0-3 keep q0 (X1), lanes 4-7 keep q1 (X2); the others just reduce q0
-                    {
-                        const bool split = lane < 8;
-                        const double s0 = split ? (h4 ? q0 : q1) : q0;
-                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, 4);
-                        q0 = (split ? (h4 ? q1 : q0) : q0) + r0;
-                    }
-                    q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
-                    q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
-                    // holders: lane 0 X1, lane 4 X2, lane 8 X3, lane 16 YS, lane 24 YN
-                    const int slot = lane == 0 ? X1 : (lane == 4 ? X2 : (lane == 8 ? X3 : (lane == 16 ? YS : (lane == 24 ? YN : -1))));
-                    if (slot >= 0) win.acc[t][slot] += q0;
-#endif
                 }
             }  // b window
-#if EXH_DEFER
             if (pend_t >= 0) reduce_pending();
-#endif
 
             accT += (accX[X1] + accX[X2]) + accX[X3];   // every expansion is in exactly one x cell: the total, once per tile
             if (xin) {   // flush the x cells of this tile
@@ -681,11 +524,8 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
         {
             double r[8];
 #pragma unroll
-            for (int k = 0; k < 5; k++) r[k] = ACC_A(k);
-            r[5] = accT; r[6] = ACC_NC0; r[7] = ACC_NC1;
-#undef ACC_A
-#undef ACC_NC0
-#undef ACC_NC1
+            for (int k = 0; k < 5; k++) r[k] = accA[k];
+            r[5] = accT; r[6] = accNC0; r[7] = accNC1;
             unsigned cnt = nconf;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {

@@ -276,6 +276,20 @@ score_batch_kernel(LocusDev L, const int* __restrict__ idx, long long n, int kma
         if (lane < kmax) v = idx[c * kmax + lane];
         const unsigned present = __ballot_sync(0xffffffffu, v >= 0);
         const int k = __popc(present);
+        // a row must list distinct union SNPs in increasing order, all below U (the reference builds its rows that way,
+        // sss_postcal.cpp:20-99); anything else is refused like a bad explicit configuration (given.cuh)
+        int prev = -1;
+        {
+            const unsigned below = present & ((1u << lane) - 1);
+            const int src = below ? 31 - __clz(below) : lane;
+            const int pv = __shfl_sync(0xffffffffu, v, src);
+            if (below) prev = pv;
+        }
+        const bool bad_row = __any_sync(0xffffffffu, v >= 0 && (v >= L.U || v <= prev));
+        if (bad_row) {
+            if (lane == 0) { flag_set(L.acc, ERR_BAD_CONFIG); if (out) out[c] = 0.0; }
+            continue;
+        }
         if (v >= 0) ws.g[__popc(present & ((1u << lane) - 1))] = L.u2i[v];
         __syncwarp();
         const bool upd = make_updates ? make_updates[c] != 0 : true;

@@ -38,6 +38,24 @@ def bind_engine_to_current_stream(engine):
     engine.set_stream(torch.cuda.current_stream().cuda_stream)
 
 
+def _order_with_torch(engine):
+    """Stream ordering between the engine's launches and what torch enqueues (NCCL collectives, clone / copy_): the
+    engine normally works on its OWN non-blocking stream, torch on its current stream, and nothing orders one after the
+    other -- an all-reduce could read the accumulator store before the exhaustive kernel has finished, and finalize
+    could run before the all-reduce has.  Every helper below that mixes the two therefore moves the engine onto torch's
+    current stream first (pipsort_set_stream waits for the work already queued on the old stream).  A no-op when the
+    caller has done so already (bind_engine_to_current_stream) or when there is no CUDA device (gloo tests)."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return
+        cur = torch.cuda.current_stream().cuda_stream
+    except Exception:
+        return
+    if hasattr(engine, "stream") and hasattr(engine, "set_stream") and engine.stream() != cur:
+        engine.set_stream(cur)
+
+
 def slice_bounds(n, world):
     """Contiguous near-equal slices of n items: bounds[r] .. bounds[r+1] belongs to rank r."""
     return [(n * r) // world for r in range(world + 1)]
@@ -85,6 +103,8 @@ def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allre
         bounds = engine.shard_ranks(c, world)
     if len(bounds) != world + 1:
         raise ValueError("need world+1 shard bounds")
+    if world > 1:
+        _order_with_torch(engine)
     engine.reset()
     engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
     if world > 1:
@@ -114,6 +134,7 @@ def score_union_configs_sharded(engine, idx, make_updates=None, group=None):
     if world == 1:
         return engine.score_union_configs(idx, mu)
     import torch
+    _order_with_torch(engine)
     b = slice_bounds(n, world)
     lo, hi = b[rank], b[rank + 1]
     mine = engine.score_union_configs(idx[lo:hi], None if mu is None else mu[lo:hi]) if hi > lo else np.zeros(0)
@@ -133,6 +154,7 @@ def read_sharded(engine, group=None):
     world, _ = world_and_rank(group)
     if world == 1:
         return engine.read()
+    _order_with_torch(engine)
     acc = engine.accumulator_tensor()
     keep = acc.clone()
     _dist().all_reduce(acc, group=group)

@@ -61,9 +61,7 @@ def lib():
     """Loads pipsort_b200/lib/libpipsort_b200.so (builds it first if the sources are newer)."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if not os.path.exists(path):
-            path = _build.build_engine()
+        path = _build.build_engine()          # rebuilds only when the library is missing or its sources changed (content hash)
         L = C.CDLL(path)
         vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
         L.pipsort_create.argtypes = [C.POINTER(_Locus), i32, C.c_uint32, C.POINTER(vp)]

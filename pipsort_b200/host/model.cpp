@@ -53,26 +53,20 @@ Model::Model(const std::vector<std::string>& ldDir, const std::vector<std::strin
     double K = 0.0;
     for (int i = 0; i < num_of_studies; i++) {
         const auto t0 = std::chrono::steady_clock::now();
-        // model.h:171-264 on the GPU (cuSOLVER LU / eigensolver + the engine's kernels); PIPSORT_HOST_PREP=1 keeps the
-        // host restatement (O(n^3) Jacobi sweeps: fine for hundreds of SNPs, hopeless for thousands)
-        Prep p;
-        const char* hp = std::getenv("PIPSORT_HOST_PREP");
-        if (hp && *hp == '1') {
-            p = preprocess_study(sigma[i], z_score[i], num_snps_all[i]);
-        } else {
-            pipsort_prep_info info;
+        // model.h:171-264 on the GPU (cuSOLVER LU / eigensolver + the engine's kernels): there is no host compute path
+        pipsort_prep_info info;
+        {
             std::vector<double> eff(sigma[i].size());
             if (pipsort_preprocess_study(device, num_snps_all[i], sigma[i].data(), z_score[i].data(), eff.data(), &info) != 0) {
                 std::cout << pipsort_last_error() << std::endl;
                 std::exit(1);
             }
             sigma[i].swap(eff);
-            p.add_diag = info.add_diag; p.K = info.K; p.min_eig = info.min_abs_eig;
         }
         const auto t1 = std::chrono::steady_clock::now();
         std::cout << "Time to make psd + eigen decomp = " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count()
-                  << "[µs] (diagonal shift " << p.add_diag << ", smallest eigenvalue " << p.min_eig << ")" << std::endl;
-        K += p.K;
+                  << "[µs] (diagonal shift " << info.add_diag << ", smallest eigenvalue " << info.min_abs_eig << ")" << std::endl;
+        K += info.K;
     }
     post = new PostCal(sigma, z_score, K, do_sss, totalCausalSNP, &snpNames, sharing_param, gamma, tau_sqr, sigma_g_squared,
                        sample_sizes, num_snps_all, idx_to_snp_map, all_snp_pos, device, configsFile, num_configs, num_groups);

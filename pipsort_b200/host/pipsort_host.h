@@ -26,15 +26,6 @@ void importSnpMap(const std::string& file, int numCols, std::vector<std::string>
                   std::vector<std::vector<int>>& remainingCols);             // util.cpp:99-126
 void export2File(const std::string& fileName, double data);                  // util.cpp:183-187 (append)
 
-// ---- host pre-processing (model.h:171-264, util.cpp:195-263) ------------------------------------------------
-// sigma: n x n row-major LD as read.  Adds the smallest multiple of 0.01 to the diagonal that makes the LU
-// determinant positive, eigen-decomposes, and returns the effective LD  Q|Omega|Q^T  (in place), K = S'^T S'
-// and the shift.  z is unchanged by the transformation (B^T S' = z).
-struct Prep { double add_diag = 0; double K = 0; double min_eig = 0; };
-Prep preprocess_study(std::vector<double>& sigma, const std::vector<double>& z, int n);
-double lu_determinant(std::vector<double> a, int n);
-void symmetric_eigen(std::vector<double>& a, int n, std::vector<double>& w);   // a <- eigenvectors (columns)
-
 // ---- PostCal (postcal.h) ----------------------------------------------------------------------------------
 class PostCal {
 public:

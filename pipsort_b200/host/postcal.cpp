@@ -86,7 +86,9 @@ PostCal::PostCal(const std::vector<std::vector<double>>& sigma_eff, const std::v
     loc.snp_map = smap.data();
     loc.gamma = gamma;
     loc.sharing_param = sharing_param;
-    loc.max_causal = MAX_causal;
+    // max_causal sizes the engine's exponent range.  computeTotalLikelihoodGivenConfigs does not bound the number of
+    // causal SNPs of a row by maxCausalSNP (postcal.cpp:400-714): on that path size the store for the most a row may hold
+    loc.max_causal = configsFile_.empty() ? MAX_causal : std::max(MAX_causal, (int)PIPSORT_KMAX);
     // PIPSORT_DEVICES=0,1,...: one process drives several GPUs -- the locus is replicated, the rank space (or the rows of
     // the explicit-configuration matrix) is split over the engines and the accumulator stores are added up (pipsort_merge)
     std::vector<int> devices;

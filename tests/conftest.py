@@ -142,3 +142,40 @@ def assert_results_match(got, want, rtol=RTOL_LL, atol_pip=ATOL_PIP):
         np.testing.assert_allclose(sx(gp, got.total), sx(want.post, want.total), atol=atol_pip, rtol=0)
         np.testing.assert_allclose(sx(got.sharedPips, got.total), sx(want.sharedPips, want.total), atol=atol_pip, rtol=0)
         np.testing.assert_allclose(sx(got.noCausal, got.total), sx(want.noCausal, want.total), atol=atol_pip, rtol=0)
+
+
+_synth_cache = {}
+
+
+def synth_locus(n, overlap=0.8, seed=20261018, sharing_param=0.75):
+    """pipsort_b200.synth.make_locus, cached per session (the 1500- and 5000-SNP loci take seconds to generate)."""
+    from pipsort_b200 import synth
+    key = (n, overlap, seed, sharing_param)
+    if key not in _synth_cache:
+        _synth_cache[key] = synth.make_locus(n, overlap=overlap, seed=seed, sharing_param=sharing_param)
+    return _synth_cache[key]
+
+
+class exh_plan_env:
+    """Force the work decomposition of the exhaustive launch (PIPSORT_EXH_BW = b-window width, PIPSORT_EXH_XCH = x tiles
+    per item; read per launch by the planner) for the duration of a with-block."""
+
+    def __init__(self, bw=None, xch=None):
+        self.want = {"PIPSORT_EXH_BW": bw, "PIPSORT_EXH_XCH": xch}
+        self.old = {}
+
+    def __enter__(self):
+        for k, v in self.want.items():
+            self.old[k] = os.environ.get(k)
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+        return self
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

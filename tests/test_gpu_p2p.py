@@ -56,3 +56,48 @@ def test_two_ranks_combine_over_peer_memory():
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(2, os.path.join(tmp, "init"), tmp), nprocs=2, join=True)
         assert os.path.exists(os.path.join(tmp, "ok0")) and os.path.exists(os.path.join(tmp, "ok1"))
+
+
+def _nccl_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pipsort_b200 import distributed as D
+    from oracle import oracle as O
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{initfile}", rank=rank, world_size=world,
+                            device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from conftest import golden
+        L = oracle_locus("small_example")
+        want = O.exhaustive(L, 3)
+        Le = oracle_locus("example", p=0.25)
+        # the engines stay on their OWN streams: the helpers must order the all-reduce after the kernels themselves
+        with engine_for(L, 3, device=rank) as e, engine_for(Le, 2, device=rank) as e2:
+            for rep in range(4):
+                r = D.compute_total_likelihood_sharded(e, 3, collective="allreduce")
+                assert r.n_configs == want.n_eval == 268
+                assert_results_match(r, want)
+                r2 = D.compute_total_likelihood_sharded(e2, 2, collective="allreduce")
+                assert r2.n_configs == 216817
+                assert_results_match(r2, golden("example_c2_p025"))
+            # one SSS neighbourhood split over the ranks, accumulators rank-partial until read_sharded
+            rng = np.random.default_rng(3)
+            idx = np.full((40, 3), -1, dtype=np.int32)
+            for i in range(1, 40):
+                k = int(rng.integers(1, 4))
+                idx[i, :k] = np.sort(rng.choice(L.U, k, replace=False))
+            want_l, want_acc = O.score_union_configs(L, idx)
+            e.reset()
+            got_l = D.score_union_configs_sharded(e, idx)
+            np.testing.assert_allclose(got_l, want_l, rtol=1e-10)
+            assert_results_match(D.read_sharded(e), want_acc)
+        open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="NCCL needs one GPU per rank")
+def test_two_ranks_nccl_allreduce_without_stream_binding():
+    """The NCCL path of distributed.py with engines left on their own streams (no bind_engine_to_current_stream)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_nccl_worker, args=(2, os.path.join(tmp, "init"), tmp), nprocs=2, join=True)
+        assert os.path.exists(os.path.join(tmp, "ok0")) and os.path.exists(os.path.join(tmp, "ok1"))

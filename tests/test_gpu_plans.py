@@ -1,0 +1,130 @@
+"""Parity of every launch shape of the exhaustive kernel with the CPU oracle (all accumulators, not only the total).
+
+The planner (csrc/exhaustive.cuh) picks the work decomposition -- b-window width, x tiles per item -- from the size of
+the rank range and of the GPU, so a small test locus only ever sees one shape.  These tests force the other shapes
+(PIPSORT_EXH_BW / PIPSORT_EXH_XCH), run the BASELINE.json loci at full size against the oracle on all host cores, and
+compare rank ranges of the saturating 1500-SNP locus with the oracle's walk over the same ranks.
+Reference loop being replaced: postcal.cpp:769-1044; accumulation :981-1030.
+Tolerances: log-likelihoods 1e-10 relative, PIPs 1e-8 absolute (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import assert_results_match, engine_for, exh_plan_env, synth_as_oracle_locus, synth_locus
+
+pytestmark = pytest.mark.gpu
+
+_oracle_cache = {}
+
+
+def oracle_range(key, L, c, lo=0, hi=None):
+    from oracle import oracle as O
+    k = (key, c, lo, hi)
+    if k not in _oracle_cache:
+        _oracle_cache[k] = O.exhaustive_omp_full(synth_as_oracle_locus(L), c, lo, hi)
+    return _oracle_cache[k]
+
+
+def test_b150c3_all_accumulators_whole_and_sharded():
+    """BASELINE.json configs[3] (150 SNPs/study, U = 180, c = 3, 12,197,751 configurations): total, postValues, noCausal,
+    sharedPips, sharedLL, notSharedLL against the oracle -- as one run, as the 2 / 4 / 8 work-weighted shards the multi-GPU
+    path hands out (accumulated on one engine), and shard by shard (snp_map order, where the oracle can walk the same
+    rank range)."""
+    from pipsort_b200 import synth
+    SL = synth_locus(150)
+    want = oracle_range("B150", SL, 3)
+    assert want.n_eval == synth.count_configs(SL.snp_map, 3) == 12197751
+    with engine_for(SL, 3) as e:
+        r = e.compute_total_likelihood(3)
+        assert r.n_configs == want.n_eval
+        assert_results_match(r, want)
+        for parts in (2, 4, 8):
+            b = e.shard_ranks(3, parts)
+            e.reset()
+            for i in range(parts):
+                e.run_exhaustive(3, b[i], b[i + 1])
+            rs = e.read()
+            assert rs.n_configs == want.n_eval
+            assert_results_match(rs, want)
+    with engine_for(SL, 3, keep_order=True) as e:
+        r = e.compute_total_likelihood(3)
+        assert_results_match(r, want)
+        b = e.shard_ranks(3, 8)
+        for i in range(8):
+            e.reset()
+            e.run_exhaustive(3, b[i], b[i + 1])
+            rs = e.read()
+            ws = oracle_range("B150", SL, 3, b[i], b[i + 1])
+            assert rs.n_configs == ws.n_eval
+            assert_results_match(rs, ws)
+
+
+SHAPES = [(bw, xch) for bw in (32, 16, 8) for xch in (1, 2, 3, 1 << 20)]
+
+
+@pytest.mark.parametrize("c", [2, 3])
+@pytest.mark.parametrize("bw,xch", SHAPES)
+def test_forced_plan_shapes(bw, xch, c):
+    """Every (b-window, x tiles per item) shape, size classes 2 and 3, both SNP orders, whole and partial rank ranges.
+    70+70 SNPs at 50 % overlap: U = 105 = 4 x tiles, all three SNP types, so multi-tile items, narrow windows, diagonal
+    and partial tiles all occur."""
+    from oracle import oracle as O
+    SL = synth_locus(70, overlap=0.5, seed=77, sharing_param=0.25)
+    U = SL.U
+    assert U == 105
+    tot = O.total_union_subsets(U, c)
+    lowc = O.total_union_subsets(U, c - 1)
+    whole = oracle_range("S70", SL, c)
+    ranges = [(0, tot // 3), (lowc + 17, lowc + 17 + (tot - lowc) // 2), (tot - 4000, tot), (lowc - 5, lowc + 40)]
+    with exh_plan_env(bw, xch):
+        with engine_for(SL, c) as e:
+            r = e.compute_total_likelihood(c)
+            assert r.n_configs == whole.n_eval
+            assert_results_match(r, whole)
+        with engine_for(SL, c, keep_order=True) as e:
+            r = e.compute_total_likelihood(c)
+            assert r.n_configs == whole.n_eval
+            assert_results_match(r, whole)
+            for lo, hi in ranges:
+                e.reset()
+                e.run_exhaustive(c, lo, hi)
+                rs = e.read()
+                ws = oracle_range("S70", SL, c, lo, hi)
+                assert rs.n_configs == ws.n_eval, (lo, hi)
+                assert_results_match(rs, ws)
+
+
+@pytest.mark.parametrize("forced", [None, (32, 1 << 20), (32, 8)])
+def test_b1500c3_rank_ranges_against_oracle(forced):
+    """The saturating locus of the roofline claim (1500 SNPs/study, U = 1800, c = 3; 1.2e10 configurations): rank ranges
+    of ~1e6 union subsets at the start of size class 3, in its middle and at its end, in snp_map order, against the
+    oracle's walk over the same ranks -- with the planner's own choice for the range and with the shapes a whole-locus
+    run uses (many x tiles per item)."""
+    from oracle import oracle as O
+    SL = synth_locus(1500)
+    U = SL.U
+    assert U == 1800
+    tot = O.total_union_subsets(U, 3)
+    low = O.total_union_subsets(U, 2)
+    n = 1000000
+    ranges = [(low - 1000, low + n), (low + (tot - low) // 2, low + (tot - low) // 2 + n), (tot - n, tot)]
+    with exh_plan_env(*(forced or (None, None))):
+        with engine_for(SL, 3, keep_order=True) as e:
+            for lo, hi in ranges:
+                e.reset()
+                e.run_exhaustive(3, lo, hi)
+                rs = e.read()
+                ws = oracle_range("B1500", SL, 3, lo, hi)
+                assert rs.n_configs == ws.n_eval, (lo, hi)
+                assert_results_match(rs, ws)
+
+
+def test_a300c2_forced_shapes():
+    """BASELINE.json configs[2] (300 SNPs/study, c = 2) through the narrow-window and multi-tile shapes as well."""
+    SL = synth_locus(300, sharing_param=0.25)
+    want = oracle_range("A300", SL, 2)
+    for bw, xch in [(16, 1), (8, 2), (32, 1 << 20)]:
+        with exh_plan_env(bw, xch):
+            with engine_for(SL, 2) as e:
+                r = e.compute_total_likelihood(2)
+                assert r.n_configs == want.n_eval == 352501
+                assert_results_match(r, want)

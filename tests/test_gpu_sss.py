@@ -9,7 +9,8 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, args_to_params, assert_results_match, engine_for, golden, oracle_locus, synth_as_oracle_locus
+from conftest import (GOLDEN, args_to_params, assert_results_match, engine_for, golden, oracle_locus, synth_as_oracle_locus,
+                      synth_locus)
 
 pytestmark = pytest.mark.gpu
 
@@ -77,7 +78,7 @@ def test_config_d_neighbourhood_5000_snps_c5():
     whole batch through additivity (two half batches == the full batch) and idempotence of re-reading."""
     from oracle import oracle as O
     from pipsort_b200 import synth
-    L = synth.make_locus(5000, overlap=0.8, seed=20261018)
+    L = synth_locus(5000)
     U, c = L.U, 5
     assert U == 6000
     strong = [int(np.argmax(np.abs(L.z[0])))]
@@ -101,3 +102,43 @@ def test_config_d_neighbourhood_5000_snps_c5():
     pick = np.sort(rng.choice(len(nbd), 48, replace=False))
     want_l, _ = O.score_union_configs(synth_as_oracle_locus(L), idx[pick])
     np.testing.assert_allclose(got[pick], want_l, rtol=1e-10)
+
+
+def test_config_d_sample_batch_accumulators_against_oracle():
+    """BASELINE.json configs[4] again: 384 neighbours sampled from the same 29,984-configuration neighbourhood (plus the
+    null configuration and the current state), scored as ONE batch on fresh accumulators -- every accumulator (total,
+    postValues, noCausal, sharedPips, sharedLL, notSharedLL) and every max-|l| value against the oracle's
+    expand_and_compute_lkl restatement (sss_postcal.cpp:447-685), with make_updates off for a quarter of the rows."""
+    from oracle import oracle as O
+    L = synth_locus(5000)
+    U, c = L.U, 5
+    strong = int(np.where(L.snp_map[0] == int(np.argmax(np.abs(L.z[0]))))[0][0])
+    cur = sorted({strong, 17, 2999, 5998})
+    nbd = neighbourhood(cur, U, c)
+    rng = np.random.default_rng(5)
+    pick = np.sort(rng.choice(len(nbd), 384, replace=False))
+    rows = [[], cur] + [nbd[i] for i in pick]
+    idx = np.full((len(rows), c), -1, dtype=np.int32)
+    for i, v in enumerate(rows):
+        idx[i, :len(v)] = v
+    upd = (rng.uniform(size=len(rows)) < 0.75).astype(np.uint8)
+    upd[:2] = 1
+    want_l, want = O.score_union_configs(synth_as_oracle_locus(L), idx, upd)
+    with engine_for(L, c) as e:
+        got_l = e.score_union_configs(idx, upd)
+        got = e.read()
+    np.testing.assert_allclose(got_l, want_l, rtol=1e-10, atol=0)
+    assert_results_match(got, want)
+
+
+def test_bad_union_configuration_is_refused():
+    """pipsort_score_union_configs validates its rows like the explicit-configuration path does: an index >= U, a repeated
+    or a descending index raise PIPSORT_E_CONFIG instead of reading out of bounds / scoring a different configuration."""
+    import pipsort_b200 as P
+    L = oracle_locus("small_example")
+    for row in ([3, 3, -1], [5, 2, -1], [1, L.U, -1], [0, 1, 40000]):
+        with engine_for(L, 3) as e:
+            with pytest.raises(P.PipsortError) as ei:
+                e.score_union_configs(np.array([[0, 4, 7], row], dtype=np.int32))
+                e.read()
+            assert ei.value.code == 6
