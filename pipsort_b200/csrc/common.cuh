@@ -82,6 +82,9 @@ struct LocusDev {
     double logprior[KMAX + 1][KMAX + 1];  // log_prior(j,a), complete (postcal.cpp:19-59)
     double neg_half_K;                    // -K/2
     double null_l;                        // -K/2 - 1 + U log(1-gamma)   (postcal.cpp:797-803)
+    double cx;                            // -K/2 + U log(1-gamma): what the prior-weighted sums leave out
+    double rho;                           // pi'(j, a+1) / pi'(j, a) = p / ((1-p)/2)   (1 when p == 0: postcal.cpp:27)
+    int lane_ok;                          // the prior factorises with a finite rho (p < 1): score_lane.cuh may be used
     const uint32_t* exptab[KMAX + 1];     // exptab[k][e] = m0 | m1 << 8 | a << 16 for expansion e of a k-subset
     AccDev acc;
 };

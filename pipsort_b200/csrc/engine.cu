@@ -23,6 +23,7 @@
 #include "sss.cuh"
 #include "p2p.cuh"
 #include "score.cuh"
+#include "score_lane.cuh"
 
 using namespace pipsort;
 
@@ -237,6 +238,7 @@ struct pipsort_engine {
     int* d_idx = nullptr; unsigned char* d_upd = nullptr; double* d_out = nullptr;
     size_t cap_idx = 0, cap_upd = 0, cap_out = 0;
     int score_smem_set = 0;
+    bool lane_smem_set = false;
     ExhScratch exh;
     bool use_reg_kernel = true;
     bool capturing = false;
@@ -673,6 +675,12 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     e->K = K_total;
     L.neg_half_K = -0.5 * K_total;
     L.null_l = (-K_total / 2 - std::sqrt(std::fabs(1.0))) + U * std::log(1.0 - gam);   // postcal.cpp:802-803
+    L.cx = -0.5 * K_total + U * std::log(1.0 - gam);
+    L.rho = p == 0.0 ? 1.0 : p / ((1.0 - p) * 0.5);
+    {
+        const double r8 = std::pow(L.rho, KMAX);
+        L.lane_ok = p < 1.0 && std::isfinite(r8) && r8 > 0.0 && std::isfinite(1.0 / r8);
+    }
 
     // ---- expansion tables: digit i of e = state of SNP i (0: study 0 only, 1: study 1 only, 2: both) ---
     // locus independent: built once per device and shared by every engine of the process
@@ -932,21 +940,43 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
 static int check_flags(pipsort_engine* e);
 static int flags_to_error(const double* counters);
 
+// One launch that scores a batch of union configurations: lane per configuration (score_lane.cuh) for up to LANE_KMAX
+// SNPs per row, warp per configuration (score.cuh) beyond that, for p == 1 and under PIPSORT_SCORE_WARP=1 (cross-check).
+// n_max bounds the batch length for the grid size; the kernel adds *d_n_extra (device) to n when given.
+static int launch_score_batch(pipsort_engine* e, const int32_t* d_idx, int64_t n, int64_t n_max, int kmax,
+                              const uint8_t* d_make_updates, double* d_out, const int* d_n_extra) {
+    static const bool force_warp = getenv("PIPSORT_SCORE_WARP") != nullptr;
+    if (kmax <= LANE_KMAX && e->L.lane_ok && !force_warp) {
+        if (!e->lane_smem_set) {
+            CU(cudaFuncSetAttribute(score_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LANE_SMEM_BYTES));
+            e->lane_smem_set = true;
+        }
+        // the warp-per-configuration fallback inside the kernel needs its shared-memory attribute as well? no: it
+        // aliases this kernel's own tables
+        const int blocks = (int)std::min<int64_t>((n_max + LANE_THREADS - 1) / LANE_THREADS, (int64_t)e->sm_count * 3);
+        score_lane_kernel<<<std::max(blocks, 1), LANE_THREADS, LANE_SMEM_BYTES, e->stream>>>(e->L, d_idx, n, kmax, d_make_updates,
+                                                                                           d_out, d_n_extra);
+    } else {
+        size_t smem = 0;
+        const int wk = std::max(kmax, 1);
+        int rc = ensure_score_smem(e, wk, &smem);
+        if (rc) return rc;
+        const int blocks = (int)std::min<int64_t>((n_max + SCORE_WARPS - 1) / SCORE_WARPS, (int64_t)e->sm_count * 8);
+        score_batch_kernel<<<std::max(blocks, 1), SCORE_WARPS * 32, smem, e->stream>>>(e->L, d_idx, n, kmax, wk, d_make_updates, d_out,
+                                                                                     d_n_extra);
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
                                        const uint8_t* d_make_updates, double* d_out) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
     if (n < 0 || kmax < 0 || kmax > e->kb) return fail(PIPSORT_E_ARG, "kmax=%d outside [0,%d]", kmax, e->kb);
     if (n == 0) return 0;
     CU(cudaSetDevice(e->device));
-    size_t smem = 0;
-    const int wk = std::max(kmax, 1);
-    int rc = ensure_score_smem(e, wk, &smem);
-    if (rc) return rc;
-    const int blocks = (int)std::min<int64_t>((n + SCORE_WARPS - 1) / SCORE_WARPS, (int64_t)e->sm_count * 8);
-    score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, d_idx, n, kmax, wk, d_make_updates, d_out, nullptr);
-    e->launches++;
-    CU(cudaGetLastError());
-    return 0;
+    return launch_score_batch(e, d_idx, n, n, kmax, d_make_updates, d_out, nullptr);
 }
 
 int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n, int kmax, const uint8_t* make_updates,
@@ -1064,11 +1094,10 @@ int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* 
         sss_lookup_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, e->stream>>>(q.tab, cur, U, c, n, kmax, q.d_out_l, q.d_batch,
                                                                                  q.d_upd, q.d_unseen, q.d_counter);
         // one launch scores the current configuration + every unseen neighbour (the batch length is read on the device)
-        const int blocks = (int)std::min<long long>((n + 1 + SCORE_WARPS - 1) / SCORE_WARPS, (long long)e->sm_count * 8);
-        score_batch_kernel<<<blocks, SCORE_WARPS * 32, smem, e->stream>>>(e->L, q.d_batch, 1, kmax, kmax, q.d_upd, q.d_scored, q.d_counter);
+        if ((rc = launch_score_batch(e, q.d_batch, 1, n + 1, kmax, q.d_upd, q.d_scored, q.d_counter))) return rc;
         sss_insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(q.tab, q.d_batch, kmax, q.d_scored, q.d_unseen, q.d_counter,
                                                                              q.d_out_l);
-        e->launches += 3;
+        e->launches += 2;
         CU(cudaGetLastError());
         int n_new = 0;
         CU(cudaMemcpyAsync(&n_new, q.d_counter, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

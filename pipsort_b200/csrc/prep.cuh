@@ -19,6 +19,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 
 #include <cusolverDn.h>
@@ -63,13 +66,30 @@ inline const CusolverApi& cusolver_api() {
     return api;
 }
 
-// dst = src + shift * I   (n x n, symmetric: row-major == column-major)
-__global__ void prep_shift_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, double shift) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t nn = (size_t)n * n;
-    if (i >= nn) return;
-    const size_t r = i / n, c = i - r * n;
-    dst[i] = src[i] + (r == c ? shift : 0.0);
+// dst (column-major, as cuSOLVER reads it) = the ROW-major src + shift * I: a tiled transpose, so that Dgetrf factorises the
+// very matrix gsl_linalg_LU_decomp does (util.cpp:205-214) -- same pivot search per column, same under/overflow pattern of
+// the determinant product -- also when the LD file is not exactly symmetric.
+__global__ void __launch_bounds__(256) prep_shift_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, double shift) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;                 // src row i, column j
+        if (i < n && j < n) tile[r][threadIdx.x] = src[(size_t)i * n + j] + (i == j ? shift : 0.0);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int j = bx + r, i = by + threadIdx.x;                 // dst column-major element (i, j) lives at dst[j * n + i]
+        if (i < n && j < n) dst[(size_t)j * n + i] = tile[threadIdx.x][r];
+    }
+}
+
+// A[i][j] = A[j][i] for j > i (row-major): gsl_eigen_symmv reads the lower triangle only (util.cpp:242), so the matrix
+// that is eigen-decomposed -- and with it the effective LD B^T B -- is the symmetric completion of the lower triangle.
+__global__ void prep_symmetrise_kernel(double* __restrict__ A, int n) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const size_t i = idx / n, j = idx - i * n;
+    if (j > i) A[idx] = A[j * n + i];
 }
 
 __global__ void prep_diag_add_kernel(double* __restrict__ A, int n, double shift) {
@@ -148,6 +168,7 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
                              unsigned long long* launches) {
     *res = PrepResult();
     if (n == 0) return 0;
+    const auto t_enter = std::chrono::steady_clock::now();
     const CusolverApi& cs = cusolver_api();
     if (!cs.ok) { *why = "cuSOLVER (libcusolver.so.11) could not be loaded"; return -1; }
     cusolverDnHandle_t h = nullptr;
@@ -182,11 +203,17 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
     PREP_CU(cudaMallocAsync(&dwork, (size_t)std::max(std::max(lw_lu, lw_ev), 1) * sizeof(double), stream));
     const unsigned blocks = (unsigned)((nn + 255) / 256);
 
+    static const bool trace = getenv("PIPSORT_TRACE_PREP") != nullptr;
+    auto tnow = [&]() { if (trace) cudaStreamSynchronize(stream); return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_setup = tnow();
+    if (trace) fprintf(stderr, "[prep] n=%d: handle + buffers %.1f ms\n", n, tms(t_enter, t_setup));
     // 1. makeSigmaPositiveSemiDefinite
     double addDiag = 0.0;
     int iters = 0;
     for (;;) {
-        prep_shift_copy_kernel<<<blocks, 256, 0, stream>>>(dA, dW, n, addDiag);
+        prep_shift_copy_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, stream>>>(dA, dW, n, addDiag);
         PREP_CS(cs.Dgetrf(h, n, n, dW, n, dwork, dipiv, dinfo));
         prep_lu_det_kernel<<<1, 32, 0, stream>>>(dW, dipiv, n, dscal);
         *launches += 2;
@@ -198,9 +225,13 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
         addDiag += 0.01;                        // accumulated exactly like util.cpp:219
         if (iters > 100000) { *why = "the LD matrix never reached a positive determinant"; cleanup(); return -3; }
     }
+    const auto t_psd = tnow();
+    if (trace) fprintf(stderr, "[prep] PSD loop: %d LU factorizations %.1f ms (shift %.2f)\n", iters, tms(t_setup, t_psd), addDiag);
     // 2. eigen-decomposition of Sigma + a I  (GSL reads the lower triangle of the row-major matrix = the upper
     //    triangle of the column-major view)
     prep_diag_add_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dA, n, addDiag);
+    prep_symmetrise_kernel<<<blocks, 256, 0, stream>>>(dA, n);
+    *launches += 2;
     PREP_CU(cudaMemcpyAsync(dW, dA, nn * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     PREP_CS(cs.Dsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, dW, n, dev, dwork, std::max(lw_ev, 1), dinfo));
     int info = 0;
@@ -212,6 +243,7 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
     double sc[3] = {0, 0, 0};
     PREP_CU(cudaMemcpyAsync(sc, dscal, sizeof sc, cudaMemcpyDeviceToHost, stream));
     PREP_CU(cudaStreamSynchronize(stream));
+    if (trace) fprintf(stderr, "[prep] eigen-decomposition + K: %.1f ms\n", tms(t_psd, tnow()));
     if (info != 0) { *why = "cusolverDnDsyevd did not converge (info " + std::to_string(info) + ")"; cleanup(); return -2; }
     if (sc[2] > 0) {
         prep_abs_fix_kernel<<<blocks, 256, 0, stream>>>(dA, dW, dev, n);

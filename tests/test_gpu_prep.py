@@ -92,3 +92,29 @@ def test_underflowing_determinant_keeps_shifting():
     assert info["psd_iterations"] == round(o_add / 0.01) + 1
     assert info["K"] == pytest.approx(o_K, rel=1e-10)
     np.testing.assert_allclose(got_sig, ld + o_add * np.eye(500), atol=1e-12)
+
+
+def test_slightly_asymmetric_ld_follows_the_reference():
+    """An LD file that is not exactly symmetric (values printed to 6 digits, estimated separately above and below the
+    diagonal): the reference LU-factorises the matrix AS READ (util.cpp:204-215) and eigen-decomposes its LOWER triangle
+    (gsl_eigen_symmv, util.cpp:242), so B^T B is the symmetric completion of the lower triangle (+ the shift).  The
+    device path must do the same: same shift, K, and an exactly symmetric effective LD equal to the oracle's."""
+    import pipsort_b200 as P
+    from oracle import oracle as O
+    from pipsort_b200 import synth
+    L = synth.make_locus(40, overlap=0.8, seed=11)
+    rng = np.random.default_rng(3)
+    for s in range(2):
+        ld = L.sigma[s].copy()
+        ld += np.triu(rng.uniform(-2e-4, 2e-4, ld.shape), 1)        # upper triangle perturbed, lower untouched
+        if s == 1:
+            ld[7] = ld[3]                                           # two identical rows: singular as read -> the loop must shift
+            ld[:, 7] = ld[:, 3]
+            ld += np.triu(rng.uniform(-1e-4, 1e-4, ld.shape), 1)
+        z = L.z[s]
+        want_sig, _, want_K, want_add, _, _ = O.preprocess(ld, z)
+        got_sig, info = P.preprocess_study(ld, z)
+        assert info["add_diag"] == want_add
+        assert np.array_equal(got_sig, got_sig.T)
+        np.testing.assert_allclose(got_sig, want_sig, rtol=0, atol=1e-11)
+        assert info["K"] == pytest.approx(want_K, rel=1e-9)
