@@ -2,19 +2,25 @@
 """bench.py -- causal configurations / second of the exhaustive posterior calculation (BASELINE.json metric).
 
 A "step" is one pass of the hot path (PostCal::computeTotalLikelihood, postcal.cpp:716-1092) over one
-synthetic locus: reset accumulators, enumerate + score every union subset of size <= c in this rank's
-shard of the rank space, combine the accumulator stores of all ranks with ONE NCCL all-reduce(sum),
-finalize (bins -> log-space results).
+synthetic locus: enumerate + score every union subset of size <= c in this rank's shard of the rank space,
+combine the accumulator stores of all ranks over NVLink peer memory (engine kernels; NCCL all-reduce as the
+fallback), finalize (bins -> log-space results).  The reset of the accumulators and the re-arming of the work
+queue are folded into the kernels that touch them last, so a pass is 2 launches on one GPU.
 
   value     whole-job configurations/s with the locus already resident in HBM, device-timed (CUDA events on
             the stream everything is launched on), max over ranks
   e2e       the same metric through the public API with HOST buffers: engine creation (H2D of LD / z / maps),
-            the pass, and the D2H read of the result arrays inside the timed region
+            the pass, and the D2H read of the result arrays inside the timed region -- the batch call over
+            distinct loci (headline) and the single-locus call (e2e.single_locus_call)
   roofline  FP64 vector-pipe roofline of the dominant kernel (the size-c class launch): algorithmic flops
-            (SURVEY.md 8d formula, counted exactly by class) / its device time / the DFMA peak measured here
+            (SURVEY.md 8d formula, counted exactly by class) / its device time / the DFMA peak measured here;
+            traffic = DRAM bytes of one launch from the ncu capture of this build (profiles/traffic.json)
   cpu_baseline   the reference's own OpenMP CPU build (oracle/_ref/PIPSORT, unmodified sources) on this host,
             on a bounded sample of the same workload (the size <= 2 prefix of the rank space, `-c 2`);
             falls back to the OpenMP port of the oracle when the reference binary is not present
+  side keys (same line): saturating (1500 SNPs/study, c=3), A300c2_p0.25 / A300c2_p0.75 (BASELINE.json configs[2]),
+            D5000c5_sss (configs[4]: one shotgun-search neighbourhood at 5000 SNPs/study, c=5, with FP64 roofline
+            fraction and LD-gather GB/s against the measured HBM bandwidth)
 
 python bench.py --impl reference ... times only the reference CPU implementation and prints the same line.
 """
@@ -42,9 +48,17 @@ WORKLOADS = {
     "A300c2": (300, 0.8, 2),
     "B1500c3": (1500, 0.8, 3),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of one exhaustive_all_kernel launch, from the `ncu --set full` captures
-# summarised in profiles/r1_v6_exhaustive_all_*.txt (the loci are L2 resident: LD and the pair tables are read from HBM once)
-TRAFFIC_BYTES = {"B150c3": 790528 + 0, "B1500c3": 39675904 + 940800}
+def traffic_for(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, as `profiles/summarize.py --traffic`
+    extracted it from the `ncu --set full` capture of the build that is benchmarked (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(workload)
+        return (int(ent["bytes"]), ent["source"]) if ent else (None, None)
+    except Exception:
+        return None, None
+
+
 METRIC = "causal configurations/sec (exhaustive, c=3, synthetic 150-SNP/study two-ancestry locus)"
 UNIT = "configs/s"
 
@@ -254,6 +268,7 @@ def main():
                     help="multi-GPU combine step: the engine's peer-memory kernels (default) or one NCCL all-reduce")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sat", action="store_true", help="skip the saturating B1500c3 side measurement")
+    ap.add_argument("--no-side", action="store_true", help="skip the A300c2 / D5000c5 side measurements (BASELINE.json configs[2], [4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -290,9 +305,16 @@ def main():
 
     collective_used = []
     graph_used = []
+    hbm_gbs = 6548.2
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_gbs = float(json.load(f).get("hbm_gbs", hbm_gbs))
+    except Exception:
+        pass
 
     def measure(L, c, steps, warmup, clocks=False):
-        """Device-timed steps on the resident locus; returns dict of timings."""
+        """Device-timed passes on the resident locus.  A pass = this rank's exhaustive launch + the combine step + the
+        finalize; the reset of the accumulators is folded into the kernels that read them last."""
         total_configs = synth.count_configs(L.snp_map, c)
         e = P.Engine(L.num_snps, L.sigma, L.z, L.d, L.K, L.snp_map, gamma=L.gamma, sharing_param=L.sharing_param,
                      max_causal=c, device=local)
@@ -307,16 +329,15 @@ def main():
         collective_used.append(coll)
 
         def step():
-            D.run_exhaustive_sharded(e, c, bounds=b, collective=coll)   # reset + this rank's launch + the combine step
-            e.finalize()
+            D.pass_exhaustive_sharded(e, c, b, collective=coll)
 
-        e.flush_l2(); step()                  # first pass: builds the pair tables, allocates the scratch buffers
+        e.reset()
+        e.flush_l2(); step()                  # first pass: builds the pair tables, uploads the work plan
         l0 = e.launch_count()
         e.flush_l2(); step()
         launches_per_step = e.launch_count() - l0
         # the pass is a fixed sequence of the engine's launches: record it once into a CUDA graph and replay it with one
-        # launch per step (the host cost of issuing ~6 launches is comparable to this 0.1 ms pass).  The NCCL fallback is
-        # issued by torch and stays un-captured.
+        # launch per step.  The NCCL fallback is issued by torch and stays un-captured.
         run = step
         graphed = False
         if coll != "allreduce" or world == 1:
@@ -330,19 +351,19 @@ def main():
         if clocks and rank == 0:
             sampler.start()                   # before the barrier: spawning nvidia-smi must not delay rank 0's first steps
         barrier()
-        evs, kms = [], []
+        evs = []
         pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         t_wall = time.perf_counter()
         for a, z in pairs:
             e.flush_l2()                      # L2 flushed between timed iterations (outside the event pair)
             a.record(stream); run(); z.record(stream)
             evs.append((a, z))
-            kms.append(None)
         barrier()
         t_wall = time.perf_counter() - t_wall
+        res = e.fetch() if rank == 0 else None            # the last timed pass: the whole job's result on the root
         if clocks:
-            # the timed region lasts a few milliseconds (20 steps of 0.07 ms): keep the SAME step running back to back for
-            # another ~0.3 s, untimed, so that nvidia-smi (20 ms period) sees the clocks / throttle reasons under this load
+            # the timed region lasts a few milliseconds: keep the SAME step running back to back for another ~0.3 s,
+            # untimed, so that nvidia-smi (20 ms period) sees the clocks / throttle reasons under this load
             t_load = time.perf_counter()
             while time.perf_counter() - t_load < 0.3:
                 for _ in range(50):
@@ -352,28 +373,35 @@ def main():
         clk = sampler.stop() if clocks and rank == 0 else None
         if clk is not None:
             clk["window"] = "timed region + 0.3 s of the same step repeated back to back (untimed), nvidia-smi every 20 ms"
-        launches = launches_per_step * steps
         ms = [a.elapsed_time(z) for a, z in evs]
         if os.environ.get("PIPSORT_BENCH_DEBUG"):
             print(f"[rank {rank}] per-step ms: " + " ".join(f"{x:.4f}" for x in ms), file=sys.stderr, flush=True)
-        # dominant-kernel duration: a few extra steps timed on the launch itself
-        for _ in range(min(steps, 10)):
+        # dominant-kernel duration: a few extra passes timed on the launch itself (CUDA events around the kernel)
+        kms = []
+        for _ in range(min(max(steps, 3), 10)):
             e.flush_l2(); step(); kms.append(e.last_kernel_ms())
-        kms = [k for k in kms if k is not None]
         tot_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
         k_ms = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
-        cnt = e.config_count()            # the count rides in the combined store: the whole job's (on the root at least)
         if world > 1:
             dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
-        res = e.read() if rank == 0 else None
-        if world > 1:
             dist.barrier()
         e.close()
         if rank == 0:
-            assert cnt == total_configs, (cnt, total_configs)
+            assert res.n_configs == total_configs, (res.n_configs, total_configs)
         return dict(total_configs=total_configs, ms_per_step=float(tot_ms.item()) / steps, kernel_ms=float(k_ms.item()),
-                    launches=launches, wall_ms_per_step=1e3 * t_wall / steps, clocks=clk, result=res)
+                    launches=launches_per_step * steps, launches_per_step=launches_per_step,
+                    wall_ms_per_step=1e3 * t_wall / steps, timed_region_s=float(tot_ms.item()) * 1e-3, clocks=clk, result=res)
+
+    def roofline_of(L, c, m, peak, workload=None):
+        (cf, cn), _ = class_flops(L.snp_map, c)
+        achieved = cf / world / (m["kernel_ms"] * 1e-3) / 1e12     # the launch on rank r covers 1/world of the class
+        tr, src = traffic_for(workload) if (workload and world == 1) else (None, None)
+        r = {"bound": "fp64", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
+             "traffic": tr, "kernel_ms": m["kernel_ms"], "flop_per_launch": cf / world, "flop_per_config": cf / max(cn, 1)}
+        if src:
+            r["traffic_source"] = src
+        return r
 
     def measure_e2e(L, c, steps, warmup):
         """Public API with HOST (pinned) buffers: create (H2D) + pass + read (D2H) + destroy, wall clock between syncs."""
@@ -382,18 +410,23 @@ def main():
         z = torch.from_numpy(np.concatenate(L.z)).pin_memory()
         h2d = sig.numel() * 8 + z.numel() * 8 + L.snp_map.size * 4 * 3 + 2 * 16
         d2h = 8 * (1 + 2 + L.N + 3 * L.U)
-
         sig_np, z_np = sig.numpy(), z.numpy()
 
+        # (a) ONE locus per call.  N = 1: pipsort_posterior_exhaustive.  N > 1: the same locus with its rank space sharded
+        # over the GPUs and the stores combined over peer memory -- every rank creates its engine from host buffers,
+        # the root reads the result.
         def once():
-            if world == 1:      # one locus, one C-ABI call: create (H2D) + exhaustive pass + read (D2H) + destroy
+            if world == 1:
                 return P.posterior_exhaustive(L.num_snps, sig_np, z_np, L.d, L.K, L.snp_map, c, gamma=L.gamma,
                                               sharing_param=L.sharing_param, device=local)
             e = P.Engine(L.num_snps, sig_np, z_np, L.d, L.K, L.snp_map, gamma=L.gamma,
                          sharing_param=L.sharing_param, max_causal=c, device=local)
-            if world > 1:
+            coll = "p2p" if (args.collective != "allreduce" and D.connect_p2p(e)) else "allreduce"
+            if coll == "allreduce":
                 D.bind_engine_to_current_stream(e)
-            r = D.compute_total_likelihood_sharded(e, c)
+            r = D.compute_total_likelihood_sharded(e, c, collective=coll)
+            if coll == "p2p":
+                dist.barrier()            # the root must have consumed the slots before a rank destroys its mailbox
             e.close()
             return r
 
@@ -408,58 +441,153 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         serial_ms = 1e3 * float(dt.item()) / steps
-        # The call a user with many loci makes -- a LIST of loci in one C-ABI call (pipsort_posterior_exhaustive_batch).
-        # Every step (= locus) still has its own pinned-host -> device copy of the LD matrices / z / maps, its own kernels
-        # and its own device -> host read of the result arrays inside the timed region; the engine overlaps the uploads and
-        # preparation of locus i+1 and the read-back of locus i-1 with the evaluation of locus i (three streams).  With
-        # several GPUs the LOCI are dealt out to the ranks (independent units, no collective): every rank runs the same
-        # call on its own list; a single 0.1 ms locus is not worth sharding (single_locus_call_ms shows that path).
+        # (b) the call a user with many loci makes -- a LIST of loci in one C-ABI call (pipsort_posterior_exhaustive_batch).
+        # Every step (= locus) has its OWN pinned host arrays (distinct objects: nothing is shared or memoised between
+        # loci), its own pinned-host -> device copy of the LD matrices / z / maps, its own kernels and its own device ->
+        # host read of the result arrays inside the timed region; the engine overlaps the uploads and preparation of locus
+        # i+1 and the read-back of locus i-1 with the evaluation of locus i (three streams).  With several GPUs the LOCI
+        # are dealt out to the ranks (independent units, no collective): every rank runs the same call on its own list.
         nb = max(steps, 8) * 4
-        locus = dict(num_snps=L.num_snps, sigma=sig_np, z=z_np, d=L.d, K=L.K, snp_map=L.snp_map, gamma=L.gamma,
-                     sharing_param=L.sharing_param)
-        P.posterior_exhaustive_batch([locus] * 8, c, device=local)
+        loci = []
+        for i in range(nb):
+            sg = sig.clone().pin_memory(); zz = z.clone().pin_memory()
+            loci.append(dict(num_snps=L.num_snps.copy(), sigma=sg.numpy(), z=zz.numpy(), d=L.d.copy(), K=L.K,
+                             snp_map=L.snp_map.copy(), gamma=L.gamma, sharing_param=L.sharing_param, _keep=(sg, zz)))
+        P.posterior_exhaustive_batch(loci[:8], c, device=local)
         barrier()
         t = time.perf_counter()
-        rs = P.posterior_exhaustive_batch([locus] * nb, c, device=local)
+        rs = P.posterior_exhaustive_batch(loci, c, device=local)
         barrier()
         dtb = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dtb, op=dist.ReduceOp.MAX)
         dtb = float(dtb.item())
         assert all(x.n_configs == total_configs for x in rs)
-        assert abs(rs[-1].total - r.total) <= 1e-9 * abs(r.total)
+        if r is not None:
+            assert abs(rs[-1].total - r.total) <= 1e-9 * abs(r.total)
         return {"value": total_configs * nb * world / dtb, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * dtb / (nb * world), "loci_per_call": nb, "loci_total": nb * world,
-                "single_locus_call_ms": serial_ms,
-                "timing": "host wall clock (max over ranks) around ONE call per rank that evaluates loci_per_call loci from pinned "
-                          "host buffers (per locus: H2D of LD / z / maps, preparation + exhaustive + finalize kernels, D2H of the "
-                          "result arrays; three loci in flight on three streams per GPU; loci dealt out to the ranks, no "
-                          "collective); single_locus_call_ms = one locus per call"
-                          + (" with its rank space sharded over the GPUs and one NCCL all-reduce" if world > 1 else "")}
+                "ms_per_step": 1e3 * dtb / (nb * world), "what": "batch call (loci_per_call distinct loci per rank in ONE C-ABI call)",
+                "loci_per_call": nb, "loci_total": nb * world,
+                "single_locus_call": {"value": total_configs / (serial_ms * 1e-3), "unit": UNIT, "ms_per_step": serial_ms,
+                                      "what": ("one locus per C-ABI call (create + pass + read + destroy)" if world == 1 else
+                                               "one locus per call, its rank space sharded over the GPUs, stores combined over peer "
+                                               "memory, result read on the root (create + pass + combine + read + destroy on every rank)")},
+                "timing": "host wall clock (max over ranks) around ONE call per rank that evaluates loci_per_call DISTINCT loci "
+                          "(own pinned host arrays each) -- per locus: H2D of LD / z / maps, preparation + exhaustive + finalize "
+                          "kernels, D2H of the result arrays; three loci in flight on three streams per GPU; loci dealt out to "
+                          "the ranks, no collective"}
+
+    def measure_sss(peak):
+        """BASELINE.json configs[4]: one neighbourhood of the stochastic shotgun search on the 5000-SNP/study locus (c = 5;
+        29,984 union configurations x up to 3^5 expansions) through pipsort_score_union_configs_device -- the launch the
+        search issues once per round (sss_postcal.cpp:223-255) -- and the whole search through pipsort_sss.  With N GPUs
+        the neighbourhood list is cut into N slices (distributed.score_union_configs_sharded_device): every rank scores
+        its slice, the max-|l| values are all-gathered."""
+        Ld = synth.make_locus(5000, overlap=0.8)
+        U, cc = Ld.U, 5
+        cur = sorted({int(np.where(Ld.snp_map[0] == int(np.argmax(np.abs(Ld.z[0]))))[0][0]), 17, U // 2 - 1, U - 2})
+        non = np.array([g for g in range(U) if g not in set(cur)], dtype=np.int32)
+        rows = []
+        for g in non:                                     # zero: added SNP outer, dropped position inner (sss_postcal.cpp:72-99)
+            for m in range(len(cur)):
+                rows.append(sorted(cur[:m] + cur[m + 1:] + [int(g)]))
+        rows += [cur[:m] + cur[m + 1:] for m in range(len(cur))]
+        rows += [sorted(cur + [int(g)]) for g in non]
+        idx = np.full((len(rows), cc), -1, dtype=np.int32)
+        for i, v in enumerate(rows):
+            idx[i, :len(v)] = v
+        t0 = time.perf_counter()
+        e = P.Engine(Ld.num_snps, Ld.sigma, Ld.z, Ld.d, Ld.K, Ld.snp_map, gamma=Ld.gamma, sharing_param=Ld.sharing_param,
+                     max_causal=cc, device=local)
+        e.sync()
+        create_s = time.perf_counter() - t0
+        stream = torch.cuda.current_stream()
+        e.set_stream(stream.cuda_stream)
+        bnd = D.slice_bounds(len(rows), world)
+        lo, hi = bnd[rank], bnd[rank + 1]
+        d_idx = torch.from_numpy(idx[lo:hi].copy()).to(dev)
+        width = max(bnd[r + 1] - bnd[r] for r in range(world))
+        d_out = torch.zeros(width, dtype=torch.float64, device=dev)
+        d_all = torch.empty(world * width, dtype=torch.float64, device=dev) if world > 1 else None
+
+        def one():
+            e.score_union_configs_device(d_idx.data_ptr(), hi - lo, cc, 0, d_out.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(d_all, d_out)
+
+        for _ in range(3):
+            one()
+        e.sync(); e.reset(); barrier()
+        reps = 10
+        evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, z in evp:
+            a.record(stream); one(); z.record(stream)
+        barrier()
+        ms = float(np.mean([a.elapsed_time(z) for a, z in evp]))
+        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms = float(t_ms.item())
+        sh = (Ld.snp_map[0] >= 0) & (Ld.snp_map[1] >= 0)
+        n_exp, flops, gather = 0, 0.0, 0
+        for v in rows:
+            a_sh = int(sh[v].sum()) if len(v) else 0
+            f, n = synth.flops_of_union_subset(a_sh, int((Ld.snp_map[0][v] >= 0).sum()) - a_sh if len(v) else 0,
+                                               int((Ld.snp_map[1][v] >= 0).sum()) - a_sh if len(v) else 0)
+            flops += f; n_exp += n
+            k0, k1 = int((Ld.snp_map[0][v] >= 0).sum()) if len(v) else 0, int((Ld.snp_map[1][v] >= 0).sum()) if len(v) else 0
+            gather += 8 * (k0 * k0 + k1 * k1)
+        # the whole search (device-resident search state), rank 0 only
+        sss = None
+        if rank == 0:
+            e.reset()
+            t1 = time.perf_counter(); rs, it, why = e.sss(cc); dt = time.perf_counter() - t1
+            t1 = time.perf_counter(); rs, it, why = e.sss(cc); dt = time.perf_counter() - t1
+            sss = {"rounds": it, "stop_reason": why, "configs": rs.n_configs, "ms_total": 1e3 * dt, "ms_per_round": 1e3 * dt / max(it, 1)}
+        if world > 1:
+            dist.barrier()
+        e.close()
+        return {"workload": f"D5000c5_sss: synthetic 5000+5000 SNPs, U={U}, c=5; ONE neighbourhood of a 4-SNP state = {len(rows)} union "
+                            f"configurations, {n_exp} expanded configurations, sliced over {world} GPU(s)",
+                "ms_per_neighbourhood": ms, "value": n_exp / (ms * 1e-3), "unit": UNIT,
+                "union_configs_per_s": len(rows) / (ms * 1e-3),
+                "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                             "frac": flops / (ms * 1e-3) / peak, "flop_per_launch": flops,
+                             "note": "algorithmic flops, SURVEY.md 8d phi(k) count per expanded configuration"},
+                "ld_gather": {"bytes": gather, "gbs": gather / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_gbs,
+                              "frac": gather / (ms * 1e-3) / 1e9 / hbm_gbs,
+                              "note": "algorithmic gather: the k x k causal sub-blocks of both studies per union configuration, 8-byte "
+                                      "words, from the 400 MB of HBM-resident LD"},
+                "l2": "not flushed: the LD (400 MB) exceeds L2 (126 MB); launches back to back, as the search issues them",
+                "create_s": create_s, "search": sss}
 
     peak = P.measure_fp64_peak(local)                      # FLOP/s, DFMA chains on every SM
     main_m = measure(L, c, args.steps, args.warmup, clocks=True)
     e2e = measure_e2e(L, c, max(3, min(args.steps, 10)), 2)
-    (cf, cn), (tf, tn) = class_flops(L.snp_map, c)
     value = main_m["total_configs"] / (main_m["ms_per_step"] * 1e-3)
-    # the dominant launch on rank r covers 1/world of the class (work-weighted shard)
-    achieved = cf / world / (main_m["kernel_ms"] * 1e-3) / 1e12
-    roof = {"bound": "fp64", "achieved": achieved, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak / 1e12),
-            "traffic": TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
-            "note": ("FP64 vector pipe (DFMA), no tensor cores / not HBM bound; achieved = ALGORITHMIC flops of the size-c class "
-                     f"({cf:.4g} flop, {cf / max(cn, 1):.1f}/configuration, SURVEY.md 8d) per launch / its CUDA-event duration "
-                     f"({main_m['kernel_ms']:.4f} ms); peak = DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
-                     "figure; nominal 37 TFLOP/s). The kernel shares Cholesky work between the expansions of a union subset, so it "
-                     "executes fewer flops than the algorithmic count: frac can exceed 1; executed FP64 pipe utilisation is in profiles/.")}
-    sat = None
-    if not args.no_sat and args.workload == "B150c3":
+    roof = roofline_of(L, c, main_m, peak, args.workload)
+    roof["note"] = ("FP64 vector pipe (DFMA), no tensor cores / not HBM bound; achieved = ALGORITHMIC flops of the size-c class "
+                    f"({roof['flop_per_launch']:.4g} flop, {roof['flop_per_config']:.1f}/configuration, SURVEY.md 8d) per launch / its "
+                    f"CUDA-event duration ({main_m['kernel_ms']:.4f} ms); peak = DFMA micro-benchmark measured in this run "
+                    "(MEASURED_PEAKS.json has no FP64 figure; nominal 37 TFLOP/s). The kernel shares Cholesky work between the "
+                    "expansions of a union subset, so it executes fewer flops than the algorithmic count: frac can exceed 1 on "
+                    "saturating loci; executed FP64 pipe utilisation is in profiles/.")
+    side = {}
+    if args.workload == "B150c3" and not args.no_sat:
         Ls = synth.make_locus(1500, overlap=0.8)
-        sm = measure(Ls, 3, 3, 1)
-        (scf, scn), _ = class_flops(Ls.snp_map, 3)
-        sach = scf / world / (sm["kernel_ms"] * 1e-3) / 1e12
-        sat = {"workload": wl_desc("B1500c3", Ls, 3), "configs": sm["total_configs"], "ms_per_step": sm["ms_per_step"],
-               "value": sm["total_configs"] / (sm["ms_per_step"] * 1e-3), "unit": UNIT,
-               "roofline": {"bound": "fp64", "achieved": sach, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": sach / (peak / 1e12)}}
+        sm = measure(Ls, 3, 3, 3)
+        side["saturating"] = {"workload": wl_desc("B1500c3", Ls, 3), "configs": sm["total_configs"], "ms_per_step": sm["ms_per_step"],
+                              "value": sm["total_configs"] / (sm["ms_per_step"] * 1e-3), "unit": UNIT,
+                              "roofline": roofline_of(Ls, 3, sm, peak, "B1500c3")}
+    if args.workload == "B150c3" and not args.no_side:
+        # BASELINE.json configs[2]: 300 SNPs/study, 80 % overlap, c = 2, p = 0.25 and 0.75, at this run's N
+        for pv in (0.25, 0.75):
+            La = synth.make_locus(300, overlap=0.8, sharing_param=pv)
+            am = measure(La, 2, 5, 3)
+            side[f"A300c2_p{pv}"] = {"workload": wl_desc("A300c2", La, 2), "configs": am["total_configs"], "ms_per_step": am["ms_per_step"],
+                                     "value": am["total_configs"] / (am["ms_per_step"] * 1e-3), "unit": UNIT,
+                                     "roofline": roofline_of(La, 2, am, peak, "A300c2")}
+        side["D5000c5_sss"] = measure_sss(peak)            # BASELINE.json configs[4]
     if rank == 0:
         cpu = None
         if not args.no_cpu and world == 1:
@@ -469,19 +597,20 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl_desc(args.workload, L, c), "configs_per_step": main_m["total_configs"],
                            "l2": "flushed between timed steps (256 MiB memset outside the per-step event pair)",
-                           "launch": ("one CUDA-graph launch per step (reset + exhaustive kernel + combine + finalize recorded once)"
-                                      if graph_used and graph_used[0] else "individual launches"),
+                           "launch": (f"one CUDA-graph launch per step ({main_m['launches_per_step']} kernels recorded once: exhaustive"
+                                      + (" + combine" if world > 1 else "") + " + finalize; accumulator reset and work-queue re-arm are "
+                                      "folded into those kernels)" if graph_used and graph_used[0] else "individual launches"),
                            "sharding": (f"rank space split into {world} work-weighted contiguous ranges; combine step per step: "
-                                        + ("non-root ranks add their non-zero accumulator bins into the root's memory over NVLink "
-                                           "(engine kernels, CUDA IPC peer memory, device-side arrival words)"
+                                        + ("non-root ranks write their accumulator stores into the root's memory over NVLink "
+                                           "(engine kernels, CUDA IPC peer memory, self-validating words)"
                                            if collective_used and collective_used[0] == "p2p" else
                                            "one NCCL all-reduce(sum) of the accumulator store")) if world > 1 else "single GPU"},
                 "clocks": main_m["clocks"], "e2e": e2e, "gpu_launches": main_m["launches"], "roofline": roof,
-                "locus_wall_ms": e2e["ms_per_step"], "wall_ms_per_step": main_m["wall_ms_per_step"]}
+                "locus_wall_ms": e2e["ms_per_step"], "wall_ms_per_step": main_m["wall_ms_per_step"],
+                "timed_region_s": main_m["timed_region_s"]}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if sat is not None:
-            line["saturating"] = sat
+        line.update(side)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

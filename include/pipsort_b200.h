@@ -131,7 +131,10 @@ int pipsort_score_union_configs(pipsort_engine* e, const int32_t* idx, int64_t n
 int pipsort_score_union_configs_device(pipsort_engine* e, const int32_t* d_idx, int64_t n, int kmax,
                                        const uint8_t* d_make_updates, double* d_out_max_abs_l);
 
-/* Replaces PostCal::computeTotalLikelihoodGivenConfigs (postcal.cpp:400-714; flags -b/-d/-e, pipsort.cpp:153-161):
+/* (The exponent range of the accumulators is sized from pipsort_locus.max_causal: create the engine with max_causal >= the
+ * largest number of causal SNPs a row may hold -- PIPSORT_KMAX covers every row this call accepts; the reference does not
+ * bound a row by maxCausalSNP.)
+ * Replaces PostCal::computeTotalLikelihoodGivenConfigs (postcal.cpp:400-714; flags -b/-d/-e, pipsort.cpp:153-161):
  * configs is the int16 matrix [num_configs][num_groups] the reference mmaps (postcal.cpp:429-447), every row ONE
  * configuration given as global SNP indices offset_s + i (postcal.cpp:868-872) in increasing order, negative =
  * unused group; rows without any entry are the null configuration (postcal.cpp:461-492).  Accumulates into the
@@ -164,6 +167,15 @@ int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out);
 /* Launches the finalize kernel only (bins -> log-space results, kept on the device); pipsort_read_accumulators
  * = pipsort_finalize + device-to-host copy + scatter into the caller's arrays.                      */
 int pipsort_finalize(pipsort_engine* e);
+
+/* pipsort_finalize that also leaves the accumulators EMPTY (the same launch zeroes every bin it has read and the
+ * counters): a driver that repeats passes -- permutation replicates, one locus after another on a resident engine --
+ * needs no pipsort_reset between them.  The results stay on the device until the next finalize;
+ * pipsort_fetch_results copies them into the caller's arrays (same layout and meaning as pipsort_read_accumulators,
+ * which would find the store empty after a pipsort_finalize_reset).  Replaces the zero-initialised result arrays of a
+ * fresh PostCal (postcal.h:129-160) + the reads of postcal.cpp:1144-1163.                            */
+int pipsort_finalize_reset(pipsort_engine* e);
+int pipsort_fetch_results(pipsort_engine* e, const pipsort_outputs* out);
 
 /* Device time (CUDA events on the engine's stream) of the dominant kernel of the last pipsort_run_exhaustive
  * call: the launch that covered the largest subset-size class.  Blocks until that launch has finished. */
@@ -218,6 +230,9 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src); /* dst += src (copi
 int pipsort_p2p_export(pipsort_engine* e, int world, void* handle);
 int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int rank, int root);
 int pipsort_p2p_reduce_to_root(pipsort_engine* e);
+/* The same, and a NON-root rank's accumulators are left empty by the very kernel that sends them (the root's are emptied
+ * by pipsort_finalize_reset): a repeated pass needs no pipsort_reset on any rank.                                 */
+int pipsort_p2p_reduce_to_root_reset(pipsort_engine* e);
 
 /* Split [0,total) into `parts` contiguous rank ranges of roughly equal work (expanded configurations
  * weighted); bounds receives parts+1 values.                                                      */

@@ -109,9 +109,10 @@ __global__ void __launch_bounds__(128) pair_tables_kernel(PairTablesArgs T) {   
 }
 
 // ---- finalize: bins -> log-space results --------------------------------------------------------------
-// warp-collective: lanes scan the bins of one accumulator in parallel, the top three non-empty bins give M 2^N
-__device__ inline XAcc bins_read_warp(const AccDev& a, int slot, int g, int lane) {
-    const double* p = bin_ptr(a, slot, g);
+// warp-collective: lanes scan the bins of one accumulator in parallel, the top three non-empty bins give M 2^N;
+// clear: leave the accumulator empty behind (the finalize kernel then doubles as the reset of the next pass)
+__device__ inline XAcc bins_read_warp(const AccDev& a, int slot, int g, int lane, bool clear = false) {
+    double* p = bin_ptr(a, slot, g);
     int top = -1;
     for (int b = lane; b < a.NB; b += 32)
         if (p[(size_t)b * a.Upad] > 0.0) top = b;
@@ -120,6 +121,10 @@ __device__ inline XAcc bins_read_warp(const AccDev& a, int slot, int g, int lane
     double M = p[(size_t)top * a.Upad];
     if (top > 0) M += p[(size_t)(top - 1) * a.Upad] * 0x1p-512;
     if (top > 1) M += (p[(size_t)(top - 2) * a.Upad] * 0x1p-512) * 0x1p-512;
+    if (clear) {
+        __syncwarp();
+        for (int b = lane; b < a.NB; b += 32) p[(size_t)b * a.Upad] = 0.0;
+    }
     const int hi = __double2hiint(M);
     const int e = ((hi >> 20) & 0x7ff) - 1023;
     M = __hiloint2double(hi - (e << 20), __double2loint(M));
@@ -154,12 +159,19 @@ __device__ inline double xlog_or_zero(const XAcc& a, double c) {
 //      postValues study 0, postValues study 1, sharedPips, sharedLL, notSharedLL
 // One warp per union SNP (plus one warp per scalar).
 constexpr int FIN_WARPS = 8;
-__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res) {
+__global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res,
+                                                                  int clear) {
+    // launched with programmatic stream serialization: the blocks may become resident while the kernel before them in
+    // the stream is still draining; nothing of the accumulator store is touched before that kernel has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x < NCOUNTER) res[3 + (size_t)5 * U + threadIdx.x] = acc.counters[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x < NCOUNTER) {
+        res[3 + (size_t)5 * U + threadIdx.x] = acc.counters[threadIdx.x];
+        if (clear) acc.counters[threadIdx.x] = 0.0;
+    }
     if (w < 3) {
-        const XAcc v = bins_read_warp(acc, SCAL, w, lane);
+        const XAcc v = bins_read_warp(acc, SCAL, w, lane, clear != 0);
         if (lane == 0) res[w] = xlog_or_zero(v, cx);
         return;
     }
@@ -169,12 +181,17 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, in
     if (acc.NB <= 32) {
         double v[5];
 #pragma unroll
-        for (int k = 0; k < 5; k++) v[k] = lane < acc.NB ? bin_ptr(acc, k, g)[(size_t)lane * acc.Upad] : 0.0;   // X1 X2 X3 YS YN
+        for (int k = 0; k < 5; k++) {   // X1 X2 X3 YS YN
+            double* q = bin_ptr(acc, k, g) + (size_t)lane * acc.Upad;
+            v[k] = lane < acc.NB ? *q : 0.0;
+            if (clear && lane < acc.NB && v[k] != 0.0) *q = 0.0;
+        }
         x1 = bins_from_lanes(v[X1], acc.bias); x2 = bins_from_lanes(v[X2], acc.bias); x3 = bins_from_lanes(v[X3], acc.bias);
         ys = bins_from_lanes(v[YS], acc.bias); yn = bins_from_lanes(v[YN], acc.bias);
     } else {
-        x1 = bins_read_warp(acc, X1, g, lane); x2 = bins_read_warp(acc, X2, g, lane); x3 = bins_read_warp(acc, X3, g, lane);
-        ys = bins_read_warp(acc, YS, g, lane); yn = bins_read_warp(acc, YN, g, lane);
+        x1 = bins_read_warp(acc, X1, g, lane, clear != 0); x2 = bins_read_warp(acc, X2, g, lane, clear != 0);
+        x3 = bins_read_warp(acc, X3, g, lane, clear != 0);
+        ys = bins_read_warp(acc, YS, g, lane, clear != 0); yn = bins_read_warp(acc, YN, g, lane, clear != 0);
     }
     if (lane >= 5) return;
     XAcc p0 = x1, p1 = x2;
@@ -401,7 +418,7 @@ void pipsort_destroy(pipsort_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->own_stream) {
         auto in_arena = [&](const void* q) { return e->arena && (const char*)q >= e->arena && (const char*)q < e->arena + e->arena_cap; };
-        if (e->exh.d_prefix && !in_arena(e->exh.d_prefix)) cudaFreeAsync(e->exh.d_prefix, e->own_stream);
+        if (e->exh.d_chunks && !in_arena(e->exh.d_chunks)) cudaFreeAsync(e->exh.d_chunks, e->own_stream);
         if (e->exh.d_counter && !in_arena(e->exh.d_counter)) cudaFreeAsync(e->exh.d_counter, e->own_stream);
         for (void* p : e->allocs) cudaFreeAsync(p, e->own_stream);   // stream-ordered: no second synchronisation needed
         if (e->arena) cudaFreeAsync(e->arena, e->own_stream);
@@ -518,6 +535,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     {
         size_t est = 64 * 256 + sizeof(LocusDev) + (size_t)(3 + 5 * U + NCOUNTER) * 8 + (size_t)(U + 2) * 8 +
                      ((size_t)NSLOT * 16 * (size_t)std::max((U + 3) & ~3, 4) + NCOUNTER) * 8;
+        est += ((size_t)e->sm_count * 12 + 256) * sizeof(int4) + 512;               // chunk descriptors of the exhaustive launch
         size_t nints = (size_t)5 * U;
         for (int s = 0; s < S; s++) {
             const size_t nr = (size_t)lc->num_snps[s], n = e->orig[s].size(), ldw = (n + 3) & ~(size_t)3;
@@ -731,11 +749,13 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     if ((rc = dev_alloc(e, &e->d_res, 3 + (size_t)5 * U + NCOUNTER))) return rc;   // results | counters: one D2H per read
     e->h_res.resize(3 + (size_t)5 * U + NCOUNTER);
     // scratch of the exhaustive launch (work-queue head, per-a item prefix) from the arena as well
-    if ((rc = dev_alloc(e, &e->exh.d_counter, 1))) return rc;
-    e->exh.cap_prefix = (size_t)U + 2;
-    if ((rc = dev_alloc(e, &e->exh.d_prefix, e->exh.cap_prefix))) return rc;
-    e->exh.pin_prefix_cap = e->exh.cap_prefix * sizeof(u64);
-    e->exh.pin_prefix = pin_slice(e, e->exh.pin_prefix_cap);
+    if ((rc = dev_alloc(e, &e->exh.d_counter, 2))) return rc;
+    CU(cudaMemsetAsync(e->exh.d_counter, 0, 2 * sizeof(unsigned), e->stream));
+    e->exh.cap_chunks = (size_t)e->sm_count * 12 + 256;     // one chunk per resident warp + singles tiles: the small-locus plan
+    if ((rc = dev_alloc(e, &e->exh.d_chunks, e->exh.cap_chunks))) return rc;
+    e->exh.chunks_in_arena = true;
+    e->exh.pin_stage_cap = e->exh.cap_chunks * sizeof(int4);
+    e->exh.pin_stage = pin_slice(e, e->exh.pin_stage_cap);
     CU(cudaMemsetAsync(acc.bins, 0, e->bins_len * sizeof(double), e->stream));
     // the caller's buffers and the local staging vectors must not be read after return: wait for the H2D copies only
     // (recorded in ev_up after the last of them); the preparation kernels and memsets keep running asynchronously.
@@ -953,7 +973,7 @@ static int launch_score_batch(pipsort_engine* e, const int32_t* d_idx, int64_t n
         }
         // the warp-per-configuration fallback inside the kernel needs its shared-memory attribute as well? no: it
         // aliases this kernel's own tables
-        const int blocks = (int)std::min<int64_t>((n_max + LANE_THREADS - 1) / LANE_THREADS, (int64_t)e->sm_count * 3);
+        const int blocks = (int)std::min<int64_t>((n_max + LANE_CFG_PER_BLOCK - 1) / LANE_CFG_PER_BLOCK, (int64_t)e->sm_count * 8);
         score_lane_kernel<<<std::max(blocks, 1), LANE_THREADS, LANE_SMEM_BYTES, e->stream>>>(e->L, d_idx, n, kmax, d_make_updates,
                                                                                            d_out, d_n_extra);
     } else {
@@ -1192,15 +1212,34 @@ static int flags_to_error(const double* c) {
     return 0;
 }
 
-int pipsort_finalize(pipsort_engine* e) {
-    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+static int finalize_launch(pipsort_engine* e, bool clear) {
     CU(cudaSetDevice(e->device));
     const int U = e->U;
     const double cy = -0.5 * e->K, cx = cy + U * std::log(1.0 - e->gamma);
-    finalize_kernel<<<(U + 3 + FIN_WARPS - 1) / FIN_WARPS, FIN_WARPS * 32, 0, e->stream>>>(e->L.acc, U, cx, cy, e->d_res);
+    static const bool no_pdl = getenv("PIPSORT_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((U + 3 + FIN_WARPS - 1) / FIN_WARPS);
+    cfg.blockDim = dim3(FIN_WARPS * 32);
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    CU(cudaLaunchKernelEx(&cfg, finalize_kernel, e->L.acc, U, cx, cy, e->d_res, clear ? 1 : 0));
     e->launches++;
-    CU(cudaGetLastError());
     return 0;
+}
+
+int pipsort_finalize(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    return finalize_launch(e, false);
+}
+
+int pipsort_finalize_reset(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    return finalize_launch(e, true);
 }
 
 int pipsort_last_kernel_ms(pipsort_engine* e, float* ms) {
@@ -1223,6 +1262,15 @@ static int read_enqueue(pipsort_engine* e) {
 }
 
 static int read_complete(pipsort_engine* e, const pipsort_outputs* out);
+
+int pipsort_fetch_results(pipsort_engine* e, const pipsort_outputs* out) {
+    if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    if (!e->h_res_pin) e->h_res_pin = reinterpret_cast<double*>(pin_slice(e, e->h_res.size() * sizeof(double)));
+    double* hres = e->h_res_pin ? e->h_res_pin : e->h_res.data();
+    CU(cudaMemcpyAsync(hres, e->d_res, e->h_res.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    return read_complete(e, out);
+}
 
 int pipsort_read_accumulators(pipsort_engine* e, const pipsort_outputs* out) {
     if (!e || !out) return fail(PIPSORT_E_ARG, "null argument");
@@ -1456,8 +1504,16 @@ int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int r
     return 0;
 }
 
+static int p2p_reduce_impl(pipsort_engine* e, bool clear_sender);
 int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    return p2p_reduce_impl(e, false);
+}
+int pipsort_p2p_reduce_to_root_reset(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    return p2p_reduce_impl(e, true);
+}
+static int p2p_reduce_impl(pipsort_engine* e, bool clear_sender) {
     pipsort_engine::P2P& q = e->p2p;
     if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
     if (q.world == 1) return 0;
@@ -1467,7 +1523,7 @@ int pipsort_p2p_reduce_to_root(pipsort_engine* e) {
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
     if (q.rank != q.root) {
         p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<ulonglong2*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
-                                                       q.peers.ctrl[q.rank], q.d_done, errf);
+                                                       q.peers.ctrl[q.rank], q.d_done, errf, clear_sender ? 1 : 0);
     } else {
         p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, reinterpret_cast<const ulonglong2*>(q.mailbox), n, slot,
                                                         q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);

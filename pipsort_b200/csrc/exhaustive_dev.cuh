@@ -19,10 +19,12 @@
 //         the results straight to the binned store.  Per-lane, divergent, rare.
 // Both regimes leave the SM as native fp64 atomic adds into the exponent-binned accumulator store (common.cuh).
 //
-// Work decomposition: item = (a, b-window, chunk of x tiles), handed out by an atomic counter; the union-
-// subset rank range [r_begin, r_end) of the C-ABI is honoured by a lexicographic predicate per lane.
+// Work decomposition (exh_plan.h): the warp-steps of a size class form one fixed sequence (a, then 32-wide windows of b,
+// then 32-wide tiles of x, then the b's of the window); a CHUNK is a contiguous run of it, handed out by an atomic counter.
+// The union-subset rank range [r_begin, r_end) of the C-ABI is honoured by a lexicographic predicate per lane.
 #pragma once
 #include "common.cuh"
+#include "exh_plan.h"
 
 namespace pipsort {
 
@@ -114,13 +116,9 @@ constexpr __host__ __device__ bool in1(int t) { return t != 0; }
 
 struct ExhParams {
     int J;                 // 2 or 3
-    int bw;                // b-window size (<= 32)
-    int xch;               // x tiles per item
+    int off;               // x tiles are aligned to the top of the SNP range: tile j covers x in [32 j - off, 32 j - off + 32)
     u64 r_begin, r_end;    // in-class rank range (lexicographic over internal order)
     int a_lo, a_hi;        // J == 3: range of a that intersects the rank range
-    const u64* item_prefix;  // [a_hi - a_lo + 2] cumulative number of items (J == 3), or [2] for J == 2
-    u64 n_items;
-    unsigned* counter;     // work-queue head
     int lo[3], hi[3];      // lexicographic bounds of the rank range: first subset in range, first subset past it
     bool partial;          // false: the whole class is in range (no per-lane predicate)
 };
@@ -248,63 +246,75 @@ struct WarpWin {
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
 
-// One work item of size class J (2 or 3): (a, b window, chunk of x tiles).  Warp-collective.
+// One chunk of size class J (2 or 3): `remaining` warp-steps starting at step t_lo of the segment (a, window at b0,
+// x tile xt), continuing through the following tiles, windows and a's.  Warp-collective.
 template <int J>
-__device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, const unsigned item, WarpWin& win,
-                                         const LocusDev* __restrict__ Lg, const int lane) {
+__device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P, int a, int b0, int xt, int t_lo, int remaining,
+                                          WarpWin& win, const LocusDev* __restrict__ Lg, const int lane) {
     constexpr bool HAS_A = (J == 3);
     const AccDev& acc = L.acc;
     const int U = L.U;
+    const int off = P.off, T1 = (U - 1 + off) >> 5;
     const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
-    {
-
-        // ---- decode the item: a, first b of the window, first x tile, number of x tiles ---------------
-        int a = -1, b0, nb, xt0, nxt;
-        {
-            u64 rem = item;
-            if (HAS_A) {
-                int lo = 0, hi = P.a_hi - P.a_lo;            // largest i with prefix[i] <= item
-                while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (P.item_prefix[mid] <= (u64)item) lo = mid; else hi = mid - 1; }
-                a = P.a_lo + lo;
-                rem = item - P.item_prefix[lo];
-            }
-            const int bfirst = a + 1, blast = U - 2;         // b in [bfirst, blast], x in (b, U-1]
-            int w = 0;
-            for (;; w++) {                                   // windows of this a, each split into x-tile chunks
-                const int wb0 = bfirst + w * P.bw;
-                const int t0 = (wb0 + 1) >> 5, t1 = (U - 1) >> 5;
-                const u64 chunks = (u64)((t1 - t0 + 1 + P.xch - 1) / P.xch);
-                if (rem < chunks) { b0 = wb0; xt0 = t0 + (int)rem * P.xch; nxt = min(P.xch, t1 - xt0 + 1); break; }
-                rem -= chunks;
-            }
-            nb = min(P.bw, blast - b0 + 1);
-        }
-
-        // ---- per-item uniform values of a ---------------------------------------------------------------
-        int ha[2] = {0, 0}, la[2] = {-1, -1};
-        double invAa[2] = {1.0, 1.0}, ua[2] = {0.0, 0.0}, v1[2] = {0.0, 0.0};
-        bool okA = true;
-        int bad = 0;
+    // chunk-lifetime accumulators (lane private, plain doubles): the scalars; a cells live as long as a does
+    double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+    unsigned nconf = 0;
+    int bad = 0;
+    int ha[2] = {0, 0}, la[2] = {-1, -1};
+    double invAa[2] = {1.0, 1.0}, ua[2] = {0.0, 0.0}, v1[2] = {0.0, 0.0};
+    bool okA = true;
+    int nstates_a = 1, nb = 0;
+    bool new_a = true, new_win = true;
+    auto flush_a = [&]() {        // a cells of the a that is being left: five sums over the warp, one atomic each
         if (HAS_A) {
+            double mine = 0.0;
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
-                la[s] = L.loc[s][a];
-                ha[s] = la[s] >= 0;
-                if (ha[s]) {
-                    invAa[s] = L.st[s].invA[la[s]];
-                    ua[s] = L.st[s].u[la[s]];
-                    const int n = L.st[s].e1n[la[s]];
-                    okA = okA && n < 440;
-                    v1[s] = scale2(L.st[s].e1m[la[s]], min(n, 900));
+            for (int k = 0; k < 5; k++) {
+                double r = accA[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                if (lane == k) mine = r;
+                accA[k] = 0.0;
+            }
+            if (lane < 5) bin_add(acc, lane, a, mine, 0);
+        }
+    };
+    auto flush_window = [&]() {   // b cells of the window that is being left
+        __syncwarp();
+        if (lane < nb) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) bin_add(acc, k, b0 + lane, win.acc[lane][k], 0);
+        }
+    };
+    while (remaining > 0) {
+        // ---- uniform values of a ------------------------------------------------------------------------------
+        if (new_a) {
+            new_a = false;
+            okA = true;
+            if (HAS_A) {
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    la[s] = L.loc[s][a];
+                    ha[s] = la[s] >= 0;
+                    invAa[s] = 1.0; ua[s] = 0.0; v1[s] = 0.0;
+                    if (ha[s]) {
+                        invAa[s] = L.st[s].invA[la[s]];
+                        ua[s] = L.st[s].u[la[s]];
+                        const int n = L.st[s].e1n[la[s]];
+                        okA = okA && n < 440;
+                        v1[s] = scale2(L.st[s].e1m[la[s]], min(n, 900));
+                    }
                 }
+                if (!okA) { v1[0] = 0.0; v1[1] = 0.0; }     // every subset with this a takes the slow path
+                nstates_a = ha[0] && ha[1] ? 3 : (ha[0] || ha[1] ? 1 : 0);
             }
         }
-        if (!okA) { v1[0] = 0.0; v1[1] = 0.0; }             // every subset of this item takes the slow path
-        const int nstates_a = HAS_A ? (ha[0] && ha[1] ? 3 : (ha[0] || ha[1] ? 1 : 0)) : 1;
 
         // ---- window table: lane t prepares b = b0 + t -----------------------------------------------------
-        __syncwarp();
-        {
+        if (new_win) {
+            new_win = false;
+            nb = min(EXH_BW, U - 1 - b0);
+            __syncwarp();
             const int b = b0 + lane;
             const bool bv = lane < nb;
             int okb = 1;
@@ -339,16 +349,12 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             win.ok[lane] = okb;
 #pragma unroll
             for (int k = 0; k < 5; k++) win.acc[lane][k] = 0.0;
+            __syncwarp();
         }
-        __syncwarp();
 
-        // ---- item-lifetime accumulators (lane private, plain doubles) ------------------------------------------
-        double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
-        unsigned nconf = 0;
-
-        for (int xt = xt0; xt < xt0 + nxt; xt++) {
-            const int x = xt * 32 + lane;
-            const bool xin = x < U;
+        {
+            const int x = xt * 32 + lane - off;
+            const bool xin = x >= 0;                                     // (the top tile ends exactly at U - 1)
             // ---- per-tile lane values of x: masks {x} (4) and {a,x} (5) ----------------------------------
             int hx[2], lx[2];
             double px[2], cx[2], rx[2], Ax[2], zx[2], v4[2], v5[2];
@@ -380,11 +386,11 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
             if (!okX) { v4[0] = 0.0; v4[1] = 0.0; v5[0] = 0.0; v5[1] = 0.0; }
             const int nstates_x = hx[0] && hx[1] ? 3 : (hx[0] || hx[1] ? 1 : 0);
             double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            const bool diag = P.partial || (b0 + nb - 1 >= xt * 32);     // some lane may be inactive at some step
+            const bool diag = P.partial || (b0 + nb - 1 + off >= xt * 32);   // some lane may be inactive at some step
             double wnext[2], pnext[2];                                   // W[b][x], E{b,x} of the NEXT step (software prefetch)
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                const int lb = win.st[s].locb[0];
+                const int lb = win.st[s].locb[t_lo];
                 const bool h = lb >= 0 && hx[s];
                 const size_t o = h ? (size_t)lb * L.st[s].ldw + lx[s] : 0;
                 wnext[s] = h ? L.st[s].W[o] : 0.0;
@@ -406,9 +412,12 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
                 }
                 if (lane < 5) win.acc[pend_t][lane] += mine;
             };
-            for (int t = 0; t < nb; t++) {
+            // steps of this segment: the b's of the window that have an x of this tile beyond them, from t_lo on, as
+            // far as the chunk reaches
+            const int t_hi = min(min(nb, xt * 32 + 31 - off - b0), t_lo + remaining);
+            remaining -= t_hi - t_lo;
+            for (int t = t_lo; t < t_hi; t++) {
                 const int b = b0 + t;
-                if (b >= xt * 32 + 31) break;                       // no x of this tile is beyond b
                 if (pend_t >= 0) reduce_pending();
                 bool active = xin;
                 if (diag) {
@@ -513,38 +522,51 @@ __device__ __forceinline__ void exh_item(const LocusDev& L, const ExhParams& P, 
 #pragma unroll
                 for (int k = 0; k < 5; k++) bin_add(acc, k, x, accX[k], 0);
             }
-        }  // x tiles
-
-        // ---- flush the item: b window, a cells, scalars -----------------------------------------------------
-        __syncwarp();
-        if (lane < nb) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) bin_add(acc, k, b0 + lane, win.acc[lane][k], 0);
-        }
-        {
-            double r[8];
-#pragma unroll
-            for (int k = 0; k < 5; k++) r[k] = accA[k];
-            r[5] = accT; r[6] = accNC0; r[7] = accNC1;
-            unsigned cnt = nconf;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int k = HAS_A ? 0 : 5; k < 8; k++) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }  // segment
+        // ---- advance: next tile, else next window, else next a --------------------------------------------------------
+        if (remaining > 0) {
+            t_lo = 0;
+            xt++;
+            if (xt > T1) {
+                flush_window();
+                b0 += EXH_BW;
+                new_win = true;
+                if (b0 > U - 2) {
+                    if (!HAS_A) { nb = 0; break; }                  // (the plan never runs past the end of the pairs)
+                    flush_a();
+                    a++;
+                    b0 = a + 1;
+                    new_a = true;
+                }
+                xt = (b0 + 1 + off) >> 5;
             }
-            {   // every lane holds all eight sums after the butterfly: lane k flushes sum k (one bin_add deep, not eight)
-                double mine = 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) if (lane == k) mine = r[k];
-                if (lane < 5) { if (HAS_A) bin_add(acc, lane, a, mine, 0); }
-                else if (lane < 8) bin_add(acc, SCAL, lane == 5 ? S_TOTAL : (lane == 6 ? S_NC0 : S_NC1), mine, 0);
-                if (lane == 0) count_add(acc, (u64)cnt);
-            }
-            if (__any_sync(0xffffffffu, bad) && lane == 0) flag_set(acc, ERR_NOT_PD);
         }
-        __syncwarp();
     }
+    // ---- end of the chunk: b window, a cells, scalars ---------------------------------------------------------------
+    flush_window();
+    {
+        double r[8];
+#pragma unroll
+        for (int k = 0; k < 5; k++) r[k] = accA[k];
+        r[5] = accT; r[6] = accNC0; r[7] = accNC1;
+        unsigned cnt = nconf;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = HAS_A ? 0 : 5; k < 8; k++) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        {   // every lane holds all eight sums after the butterfly: lane k flushes sum k (one bin_add deep, not eight)
+            double mine = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (lane == k) mine = r[k];
+            if (lane < 5) { if (HAS_A) bin_add(acc, lane, a, mine, 0); }
+            else if (lane < 8) bin_add(acc, SCAL, lane == 5 ? S_TOTAL : (lane == 6 ? S_NC0 : S_NC1), mine, 0);
+            if (lane == 0) count_add(acc, (u64)cnt);
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) flag_set(acc, ERR_NOT_PD);
+    }
+    __syncwarp();
 }
 
 // Size class 1: one lane per union SNP of a 32-wide tile; three expansions at most.  Mantissa/exponent
@@ -582,16 +604,14 @@ __device__ inline void singles_tile(const LocusDev& L, int tile, int x_lo, int x
     if (lane == 0 && cnt) count_add(acc, (u64)cnt);
 }
 
-// All size classes 0..3 of one pipsort_run_exhaustive call in ONE launch: a single work queue whose items
-// are ordered from expensive (triples) to cheap (pairs, tiles of singles, the null configuration).
+// All size classes 0..3 of one pipsort_run_exhaustive call in ONE launch: a single work queue of chunk descriptors
+// (exh_plan.h), ordered from expensive (triples) to cheap (pairs, tiles of singles, the null configuration).
 struct ExhAll {
     ExhParams p3, p2;
-    u64 n3, n2;            // number of items of the two register classes
-    int n1_tiles, tile1_0; // size class 1: tiles [tile1_0, tile1_0 + n1_tiles), SNPs [x1_lo, x1_hi)
-    int x1_lo, x1_hi;
-    int do_null;           // rank 0 (the empty configuration) is in range
-    u64 n_total;
-    unsigned* counter;
+    const int4* chunks;    // [n_total] ExhChunkDesc
+    int x1_lo, x1_hi;      // size class 1: SNPs [x1_lo, x1_hi)
+    unsigned n_total;
+    unsigned* counter;     // work-queue head; [1]: blocks that have finished (the last one re-arms the queue)
 };
 
 __global__ void __launch_bounds__(EXH_WARPS * 32, EXH_MINBLOCKS)
@@ -603,13 +623,16 @@ exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(A.counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
-        if ((u64)item >= A.n_total) break;
-        if ((u64)item < A.n3) {
-            exh_item<3>(L, A.p3, item, win, Lg, lane);
-        } else if ((u64)item < A.n3 + A.n2) {
-            exh_item<2>(L, A.p2, (unsigned)(item - A.n3), win, Lg, lane);
-        } else if ((u64)item < A.n3 + A.n2 + (u64)A.n1_tiles) {
-            singles_tile(L, A.tile1_0 + (int)(item - A.n3 - A.n2), A.x1_lo, A.x1_hi, lane);
+        if (item >= A.n_total) break;
+        const int4 d = __ldg(A.chunks + item);
+        const unsigned kind = (unsigned)d.w >> 28;
+        const int nsteps = d.w & 0x0fffffff, xt = d.z & 0xffff, t_lo = (unsigned)d.z >> 16;
+        if (kind == 3) {
+            exh_chunk<3>(L, A.p3, d.x, d.y, xt, t_lo, nsteps, win, Lg, lane);
+        } else if (kind == 2) {
+            exh_chunk<2>(L, A.p2, -1, d.y, xt, t_lo, nsteps, win, Lg, lane);
+        } else if (kind == 1) {
+            singles_tile(L, d.x, A.x1_lo, A.x1_hi, lane);
         } else if (lane == 0) {   // postcal.cpp:793-822: -K/2 - 1 + U log(1-gamma)
             const double einv = 0.36787944117144233;
             bin_add(L.acc, SCAL, S_TOTAL, einv, 0);
@@ -617,6 +640,15 @@ exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
             bin_add(L.acc, SCAL, S_NC1, einv, 0);
             count_add(L.acc, 1ull);
         }
+    }
+    // this block has no more work: a dependent launch (finalize, launched with programmatic stream serialization) may
+    // start becoming resident; it still waits for the whole grid before it reads the accumulators
+    asm volatile("griddepcontrol.launch_dependents;");
+    // the last block to get here re-arms the queue for the next launch (no memset node between passes)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(A.counter + 1, 1u);
+        if (done == gridDim.x - 1) { A.counter[0] = 0u; A.counter[1] = 0u; }
     }
 }
 

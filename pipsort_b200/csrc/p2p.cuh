@@ -40,8 +40,8 @@ __device__ inline bool p2p_spin_ge(const volatile u64* p, u64 target) {
 }
 
 __global__ void __launch_bounds__(256)
-p2p_push_kernel(const double* __restrict__ store, size_t n, ulonglong2* __restrict__ my_slot_at_root, u64* __restrict__ my_ctrl,
-                unsigned* __restrict__ done, double* __restrict__ err_flag) {
+p2p_push_kernel(double* __restrict__ store, size_t n, ulonglong2* __restrict__ my_slot_at_root, u64* __restrict__ my_ctrl,
+                unsigned* __restrict__ done, double* __restrict__ err_flag, int clear) {
     __shared__ int ok;
     __shared__ u64 epoch_s;
     // the epoch lives in device memory (control word 2, bumped by the last block) so that the launch has no per-step
@@ -56,6 +56,7 @@ p2p_push_kernel(const double* __restrict__ store, size_t n, ulonglong2* __restri
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
             const u64 b = (u64)__double_as_longlong(store[i]);
             my_slot_at_root[i] = make_ulonglong2((b & 0xffffffffull) | flag, (b >> 32) | flag);
+            if (clear && b) store[i] = 0.0;          // what has been sent is gone: the push doubles as this rank's reset
         }
     }
     __syncthreads();

@@ -112,6 +112,29 @@ def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allre
     return bounds
 
 
+def pass_exhaustive_sharded(engine, c, bounds, collective="p2p", root=0, group=None):
+    """One REPEATABLE pass on accumulators that are already empty (a fresh engine, or the previous pass of this function):
+    this rank's share of computeTotalLikelihood, the combine step and the finalize, with every reset folded into the
+    kernels that read the store last -- the non-root ranks' push empties their stores, the root's finalize empties its
+    own.  Two launches on the root (three with the merge), two on the others; asynchronous; the root's results are then
+    read with engine.fetch().  collective="allreduce" keeps an explicit reset (NCCL reads and writes the store itself)."""
+    world, rank = world_and_rank(group)
+    if world == 1:
+        engine.run_exhaustive(c, bounds[0], bounds[1])
+        engine.finalize(reset=True)
+        return
+    if collective == "p2p":
+        engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
+        engine.p2p_reduce_to_root(reset_sender=True)
+        if rank == root:
+            engine.finalize(reset=True)
+        return
+    _order_with_torch(engine)
+    engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
+    _dist().all_reduce(engine.accumulator_tensor(), group=group)
+    engine.finalize(reset=True)
+
+
 def compute_total_likelihood_sharded(engine, c=None, group=None, bounds=None, collective="allreduce", root=0):
     """PostCal::computeTotalLikelihood (postcal.cpp:716) with the rank space sharded over the group.  With
     collective="p2p" only the root returns Results (the other ranks return None)."""

@@ -85,6 +85,8 @@ def lib():
         L.pipsort_sss_reset.argtypes = [vp]
         L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
         L.pipsort_finalize.argtypes = [vp]
+        L.pipsort_finalize_reset.argtypes = [vp]
+        L.pipsort_fetch_results.argtypes = [vp, C.POINTER(_Outputs)]
         L.pipsort_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.pipsort_config_count.argtypes = [vp, C.POINTER(u64)]
         L.pipsort_last_read_config_count.argtypes = [vp, C.POINTER(u64)]
@@ -99,6 +101,7 @@ def lib():
         L.pipsort_p2p_export.argtypes = [vp, i32, C.c_char_p]
         L.pipsort_p2p_connect.argtypes = [vp, C.c_char_p, i32, i32, i32]
         L.pipsort_p2p_reduce_to_root.argtypes = [vp]
+        L.pipsort_p2p_reduce_to_root_reset.argtypes = [vp]
         L.pipsort_shard_ranks_for_map.argtypes = [C.POINTER(C.c_int32), C.c_int32, i32, i32, C.c_uint32, C.POINTER(u64)]
         L.pipsort_stream.argtypes = [vp]
         L.pipsort_stream.restype = vp
@@ -270,6 +273,9 @@ class Engine:
         return self.read(), int(it.value), int(why.value)
 
     def read(self) -> Results:
+        return self._read(lib().pipsort_read_accumulators)
+
+    def _read(self, fn) -> Results:
         total = np.zeros(1)
         post = np.zeros(self.N)
         nc = np.zeros(self.S)
@@ -277,13 +283,19 @@ class Engine:
         sl = np.zeros(self.U)
         nl = np.zeros(self.U)
         o = _Outputs(_dp(total), _dp(post), _dp(nc), _dp(sp), _dp(sl), _dp(nl))
-        _check(lib().pipsort_read_accumulators(self._h, C.byref(o)))
+        _check(fn(self._h, C.byref(o)))
         cnt = C.c_uint64()
         _check(lib().pipsort_last_read_config_count(self._h, C.byref(cnt)))
         return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
 
-    def finalize(self):
-        _check(lib().pipsort_finalize(self._h))
+    def finalize(self, reset=False):
+        """Bins -> log-space results on the device; reset=True also leaves the accumulators empty (no reset() needed before
+        the next pass; fetch() then returns the results)."""
+        _check(lib().pipsort_finalize_reset(self._h) if reset else lib().pipsort_finalize(self._h))
+
+    def fetch(self) -> Results:
+        """The results of the last finalize (device -> host), without touching the accumulators."""
+        return self._read(lib().pipsort_fetch_results)
 
     def last_kernel_ms(self):
         ms = C.c_float()
@@ -338,8 +350,8 @@ class Engine:
         assert len(blob) == IPC_HANDLE_BYTES * len(handles)
         _check(lib().pipsort_p2p_connect(self._h, blob, len(handles), int(rank), int(root)))
 
-    def p2p_reduce_to_root(self):
-        _check(lib().pipsort_p2p_reduce_to_root(self._h))
+    def p2p_reduce_to_root(self, reset_sender=False):
+        _check(lib().pipsort_p2p_reduce_to_root_reset(self._h) if reset_sender else lib().pipsort_p2p_reduce_to_root(self._h))
 
     def shard_ranks(self, c, parts):
         b = (C.c_uint64 * (parts + 1))()

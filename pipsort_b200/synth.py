@@ -92,6 +92,28 @@ def flops_per_config_total(snp_map, c):
     return total, nconf
 
 
+def flops_of_union_subset(a, b0, b1):
+    """(algorithmic flops, expanded configurations) of ONE union subset with a shared, b0 study-0-only and b1 study-1-only
+    SNPs -- the per-configuration count of flops_per_config_total."""
+    from math import comb
+
+    def phi(k):
+        return 0.0 if k == 0 else k ** 3 / 3.0 + 2.5 * k * k + 31.0 / 6.0 * k + 2.0
+
+    j = a + b0 + b1
+    if j == 0:
+        return 8.0, 1          # the null configuration: prior, shift, exp + three accumulator adds
+    total, n = 0.0, 0
+    for x in range(a + 1):
+        for y in range(a + 1 - x):
+            both = a - x - y
+            mult = comb(a, x) * comb(a - x, y)
+            k0, k1 = x + both + b0, y + both + b1
+            total += mult * (phi(k0) + phi(k1) + 5 + (1 + (k0 == 0) + (k1 == 0) + k0 + k1 + 2 * j))
+            n += mult
+    return total, n
+
+
 def _block_ld(rng, n, n_ref):
     G = np.empty((n_ref, n))
     i = 0

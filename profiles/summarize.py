@@ -8,6 +8,34 @@ import csv
 import subprocess
 import sys
 
+import json
+import os
+
+if sys.argv[1] == "--traffic":
+    # python profiles/summarize.py --traffic WORKLOAD gpurun_out/x.ncu-rep kernel_substring profiles/<summary>.txt
+    #   -> records dram__bytes_read.sum + dram__bytes_write.sum of the first matching launch in profiles/traffic.json
+    _, _, wl, rep, ksub, src = sys.argv[:6]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in data:
+        if ksub in r[ik]:
+            b = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+            try:
+                with open(path) as f:
+                    tab = json.load(f)
+            except Exception:
+                tab = {}
+            tab[wl] = {"bytes": int(round(b)), "source": src, "kernel": r[ik].split("(")[0]}
+            with open(path, "w") as f:
+                json.dump(tab, f, indent=1, sort_keys=True)
+            print(wl, tab[wl])
+            break
+    sys.exit(0)
+
 rep, kern = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else None)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))

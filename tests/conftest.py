@@ -157,11 +157,11 @@ def synth_locus(n, overlap=0.8, seed=20261018, sharing_param=0.75):
 
 
 class exh_plan_env:
-    """Force the work decomposition of the exhaustive launch (PIPSORT_EXH_BW = b-window width, PIPSORT_EXH_XCH = x tiles
-    per item; read per launch by the planner) for the duration of a with-block."""
+    """Force the work decomposition of the exhaustive launch for the duration of a with-block: PIPSORT_EXH_CHUNK = target
+    cost of a chunk in warp-steps (read per launch by the planner, csrc/exhaustive.cuh; None = the planner's own choice)."""
 
-    def __init__(self, bw=None, xch=None):
-        self.want = {"PIPSORT_EXH_BW": bw, "PIPSORT_EXH_XCH": xch}
+    def __init__(self, chunk=None):
+        self.want = {"PIPSORT_EXH_CHUNK": chunk}
         self.old = {}
 
     def __enter__(self):

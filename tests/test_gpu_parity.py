@@ -371,3 +371,24 @@ def test_out_of_range_locus_is_refused():
         P.Engine([1, 1], [np.ones((1, 1)), np.ones((1, 1))], [np.array([1e6]), np.array([1.0])], [257.0, 5.72], 1.0,
                  np.zeros((2, 1), dtype=np.int32), max_causal=3)
     assert ei.value.code == 4
+
+
+@pytest.mark.parametrize("dataset,c,p", [("small_example", 3, 0.75), ("example", 2, 0.25)])
+def test_finalize_reset_and_fetch(dataset, c, p):
+    """pipsort_finalize_reset: bins -> results AND an empty store in one launch (few bins: lane-per-bin path; tests/example:
+    ~80 bins per accumulator, the scanning path); pipsort_fetch_results returns what the last finalize produced.  Passes
+    repeated without pipsort_reset must not pile up."""
+    from oracle import oracle as O
+    L = oracle_locus(dataset, p=p)
+    want = O.exhaustive(L, c) if dataset == "small_example" else golden("example_c2_p025")
+    with engine_for(L, c) as e:
+        for rep in range(3):
+            e.run_exhaustive(c)
+            e.finalize(reset=True)
+            r = e.fetch()
+            assert r.n_configs == (268 if dataset == "small_example" else 216817)
+            assert_results_match(r, want)
+        empty = e.read()                               # the store is empty now
+        assert empty.n_configs == 0 and empty.total == 0.0
+        assert not empty.postValues.any() and not empty.sharedLL.any() and not empty.noCausal.any()
+        assert_results_match(e.fetch(), empty)         # ... and fetch returns the last finalize (that of read())

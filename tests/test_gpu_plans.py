@@ -1,9 +1,11 @@
 """Parity of every launch shape of the exhaustive kernel with the CPU oracle (all accumulators, not only the total).
 
-The planner (csrc/exhaustive.cuh) picks the work decomposition -- b-window width, x tiles per item -- from the size of
-the rank range and of the GPU, so a small test locus only ever sees one shape.  These tests force the other shapes
-(PIPSORT_EXH_BW / PIPSORT_EXH_XCH), run the BASELINE.json loci at full size against the oracle on all host cores, and
-compare rank ranges of the saturating 1500-SNP locus with the oracle's walk over the same ranks.
+The planner (csrc/exhaustive.cuh, csrc/exh_plan.h) cuts the fixed sequence of warp-steps of a size class into chunks
+whose cost it picks from the size of the rank range and of the GPU, so a small test locus only ever sees one shape.  These
+tests force the other shapes (PIPSORT_EXH_CHUNK: chunks of 1, 2, 5 ... steps that end in the middle of a window, chunks that
+span several x tiles, windows and first SNPs, one chunk for everything), run the BASELINE.json loci at full size against
+the oracle on all host cores, and compare rank ranges of the saturating 1500-SNP locus with the oracle's walk over the
+same ranks.
 Reference loop being replaced: postcal.cpp:769-1044; accumulation :981-1030.
 Tolerances: log-likelihoods 1e-10 relative, PIPs 1e-8 absolute (BASELINE.json north_star)."""
 import numpy as np
@@ -58,15 +60,15 @@ def test_b150c3_all_accumulators_whole_and_sharded():
             assert_results_match(rs, ws)
 
 
-SHAPES = [(bw, xch) for bw in (32, 16, 8) for xch in (1, 2, 3, 1 << 20)]
+CHUNKS = [1, 2, 5, 13, 33, 70, 300, 5000, 1 << 26]
 
 
 @pytest.mark.parametrize("c", [2, 3])
-@pytest.mark.parametrize("bw,xch", SHAPES)
-def test_forced_plan_shapes(bw, xch, c):
-    """Every (b-window, x tiles per item) shape, size classes 2 and 3, both SNP orders, whole and partial rank ranges.
-    70+70 SNPs at 50 % overlap: U = 105 = 4 x tiles, all three SNP types, so multi-tile items, narrow windows, diagonal
-    and partial tiles all occur."""
+@pytest.mark.parametrize("chunk", CHUNKS)
+def test_forced_plan_shapes(chunk, c):
+    """Every chunk shape, size classes 2 and 3, both SNP orders, whole and partial rank ranges.  70+70 SNPs at 50 %
+    overlap: U = 105 = 4 x tiles (the lowest one partly empty: tiles are aligned to the top), all three SNP types, so
+    chunks cut inside a segment, chunks over several tiles / windows / first SNPs, diagonal and partial tiles all occur."""
     from oracle import oracle as O
     SL = synth_locus(70, overlap=0.5, seed=77, sharing_param=0.25)
     U = SL.U
@@ -75,7 +77,7 @@ def test_forced_plan_shapes(bw, xch, c):
     lowc = O.total_union_subsets(U, c - 1)
     whole = oracle_range("S70", SL, c)
     ranges = [(0, tot // 3), (lowc + 17, lowc + 17 + (tot - lowc) // 2), (tot - 4000, tot), (lowc - 5, lowc + 40)]
-    with exh_plan_env(bw, xch):
+    with exh_plan_env(chunk):
         with engine_for(SL, c) as e:
             r = e.compute_total_likelihood(c)
             assert r.n_configs == whole.n_eval
@@ -93,12 +95,12 @@ def test_forced_plan_shapes(bw, xch, c):
                 assert_results_match(rs, ws)
 
 
-@pytest.mark.parametrize("forced", [None, (32, 1 << 20), (32, 8)])
+@pytest.mark.parametrize("forced", [None, 1400, 40])
 def test_b1500c3_rank_ranges_against_oracle(forced):
     """The saturating locus of the roofline claim (1500 SNPs/study, U = 1800, c = 3; 1.2e10 configurations): rank ranges
     of ~1e6 union subsets at the start of size class 3, in its middle and at its end, in snp_map order, against the
-    oracle's walk over the same ranks -- with the planner's own choice for the range and with the shapes a whole-locus
-    run uses (many x tiles per item)."""
+    oracle's walk over the same ranks -- with the planner's own choice for the range, with the chunk size a whole-locus
+    run uses (~1400 steps: dozens of x tiles per chunk) and with small chunks."""
     from oracle import oracle as O
     SL = synth_locus(1500)
     U = SL.U
@@ -107,7 +109,7 @@ def test_b1500c3_rank_ranges_against_oracle(forced):
     low = O.total_union_subsets(U, 2)
     n = 1000000
     ranges = [(low - 1000, low + n), (low + (tot - low) // 2, low + (tot - low) // 2 + n), (tot - n, tot)]
-    with exh_plan_env(*(forced or (None, None))):
+    with exh_plan_env(forced):
         with engine_for(SL, 3, keep_order=True) as e:
             for lo, hi in ranges:
                 e.reset()
@@ -119,11 +121,11 @@ def test_b1500c3_rank_ranges_against_oracle(forced):
 
 
 def test_a300c2_forced_shapes():
-    """BASELINE.json configs[2] (300 SNPs/study, c = 2) through the narrow-window and multi-tile shapes as well."""
+    """BASELINE.json configs[2] (300 SNPs/study, c = 2) through small, medium and single-chunk plans as well."""
     SL = synth_locus(300, sharing_param=0.25)
     want = oracle_range("A300", SL, 2)
-    for bw, xch in [(16, 1), (8, 2), (32, 1 << 20)]:
-        with exh_plan_env(bw, xch):
+    for chunk in (3, 50, 1 << 26):
+        with exh_plan_env(chunk):
             with engine_for(SL, 2) as e:
                 r = e.compute_total_likelihood(2)
                 assert r.n_configs == want.n_eval == 352501
