@@ -156,6 +156,14 @@ int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_confi
  * Accumulates into the engine's accumulators (call pipsort_reset first for a fresh PostCal); *iterations receives the
  * number of completed rounds, *stop_reason 0 = max_iterations reached, 1 = break condition, 2 = convergence.     */
 int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* iterations, int32_t* stop_reason);
+/* The same search with every round's neighbourhood split over the GPUs of a group (the loop the reference
+ * parallelises with OpenMP, sss_postcal.cpp:223-255).  One process per GPU; every rank has created its engine from the
+ * same locus and called pipsort_p2p_export / pipsort_p2p_connect; all ranks call this function with the same arguments.
+ * Every rank keeps a replica of the explored-configuration table and follows the same trajectory (same seed, same
+ * values); of a round's unseen neighbours rank r expands + scores + accumulates those with index r (mod world), the
+ * max-|l| values go to every peer through the mailboxes (device-side stores over NVLink, no collective library).  The
+ * accumulators stay RANK-PARTIAL: combine them afterwards (pipsort_p2p_reduce_to_root, then read on the root).        */
+int pipsort_sss_sharded(pipsort_engine* e, int max_causal, int max_iterations, int32_t* iterations, int32_t* stop_reason);
 /* Forget the explored configurations (pipsort_sss does this itself when it starts). */
 int pipsort_sss_reset(pipsort_engine* e);
 

@@ -267,6 +267,8 @@ struct pipsort_engine {
         u64 count = 0;              // entries in the table
         double* d_out_l = nullptr; int* d_batch = nullptr; unsigned char* d_upd = nullptr; int* d_unseen = nullptr;
         int* d_counter = nullptr; double* d_scored = nullptr;
+        unsigned char* d_state = nullptr; int* d_pos_of = nullptr; double* d_total = nullptr;   // sharded search only
+        u64 epoch = 0;              // rounds of the sharded search since the engine was created (flags of the exchange)
         double* h_out_l = nullptr;  // pinned: [n_max] neighbour values + 1 slot reused for the counter
         long long n_max = 0; int kmax = 0;
     } sss;
@@ -425,7 +427,8 @@ void pipsort_destroy(pipsort_engine* e) {
     }
     {
         pipsort_engine::Sss& q = e->sss;
-        void* ps[] = {q.tab.klo, q.tab.khi, q.tab.val, q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored};
+        void* ps[] = {q.tab.klo, q.tab.khi, q.tab.val, q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored,
+                      q.d_state, q.d_pos_of, q.d_total};
         for (void* p : ps) if (p) cudaFree(p);
         if (q.h_out_l) cudaFreeHost(q.h_out_l);
     }
@@ -960,6 +963,16 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
 static int check_flags(pipsort_engine* e);
 static int flags_to_error(const double* counters);
 
+// mailbox layout: world slots of slot_len 16-byte elements | 8 control words.  A slot = the accumulator store (bins_len
+// rounded up to 16) followed by two halves (even / odd rounds) for the shotgun search's per-round exchange: the values of
+// up to n_max neighbours + the bins of the running total.
+static size_t p2p_acc_len(const pipsort_engine* e) { return (e->bins_len + 15) & ~(size_t)15; }
+static size_t p2p_sss_half(const pipsort_engine* e) {
+    const size_t n_max = (size_t)e->U * std::max(e->kb, 1) + e->kb + e->U + 1;
+    return (n_max + (size_t)e->L.acc.NB + 15) & ~(size_t)15;
+}
+static size_t p2p_slot_len(const pipsort_engine* e) { return p2p_acc_len(e) + 2 * p2p_sss_half(e); }
+
 // One launch that scores a batch of union configurations: lane per configuration (score_lane.cuh) for up to LANE_KMAX
 // SNPs per row, warp per configuration (score.cuh) beyond that, for p == 1 and under PIPSORT_SCORE_WARP=1 (cross-check).
 // n_max bounds the batch length for the grid size; the kernel adds *d_n_extra (device) to n when given.
@@ -1033,6 +1046,14 @@ int pipsort_score_given_configs_device(pipsort_engine* e, const int16_t* d_confi
 }
 
 // ---- stochastic shotgun search -----------------------------------------------------------------------------
+// first round whose running total is consulted by the convergence rule (sss_postcal.cpp:265-270: "iter >= 100" compares the
+// totals after rounds 99 and 100).  The reference's value unless PIPSORT_SSS_CONV_FROM overrides it: the search of every
+// locus we have seen ends long before round 100, so the tests lower the threshold to exercise that path.
+static int sss_conv_from() {
+    const char* v = getenv("PIPSORT_SSS_CONV_FROM");
+    return v ? std::max(0, atoi(v)) : 99;
+}
+
 static int sss_table_alloc(SssTable* t, u64 cap, cudaStream_t st) {
     t->mask = cap - 1;
     CU(cudaMalloc(&t->klo, cap * sizeof(u64)));
@@ -1081,17 +1102,18 @@ int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* 
     const int kmax = std::max(c, 1);
     const long long n_max = (long long)U * std::max(c, 1) + c + U + 1;
     if (q.n_max < n_max || q.kmax != kmax) {
-        void* ps[] = {q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored};
+        void* ps[] = {q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored, q.d_state, q.d_pos_of, q.d_total};
         for (void* p : ps) if (p) cudaFree(p);
+        q.d_state = nullptr; q.d_pos_of = nullptr; q.d_total = nullptr;
         if (q.h_out_l) cudaFreeHost(q.h_out_l);
         q.h_out_l = nullptr;
         CU(cudaMalloc(&q.d_out_l, (size_t)(n_max + 1) * sizeof(double)));
         CU(cudaMalloc(&q.d_batch, (size_t)(n_max + 1) * kmax * sizeof(int)));
         CU(cudaMalloc(&q.d_upd, (size_t)(n_max + 1)));
         CU(cudaMalloc(&q.d_unseen, (size_t)n_max * sizeof(int)));
-        CU(cudaMalloc(&q.d_counter, sizeof(int)));
+        CU(cudaMalloc(&q.d_counter, 2 * sizeof(int)));
         CU(cudaMalloc(&q.d_scored, (size_t)(n_max + 1) * sizeof(double)));
-        CU(cudaMallocHost(&q.h_out_l, (size_t)(n_max + 1) * sizeof(double)));
+        CU(cudaMallocHost(&q.h_out_l, (size_t)(n_max + 2) * sizeof(double)));
         q.n_max = n_max; q.kmax = kmax;
     }
     int rc = pipsort_sss_reset(e);
@@ -1099,6 +1121,7 @@ int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* 
     size_t smem = 0;
     if ((rc = ensure_score_smem(e, kmax, &smem))) return rc;
 
+    const int conv_from = sss_conv_from();
     std::mt19937 gen(12345);                                             // sss_postcal.cpp:138
     SssCur cur;
     memset(&cur, 0, sizeof cur);                                         // causal_locs starts empty (:115)
@@ -1127,11 +1150,11 @@ int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* 
         // (the reference inserts the new values after this check and the next one; the table already holds them, which
         //  is unobservable: both exits leave the loop)
         q.count += (u64)n_new;
-        if (iter >= 99) {                                                // the running sum is only consulted from here on
+        if (iter >= conv_from) {                                         // the running sum is only consulted from here on
             pipsort_outputs o = {&sss_sum_lkl, nullptr, nullptr, nullptr, nullptr, nullptr};
             if ((rc = pipsort_read_accumulators(e, &o))) return rc;
         }
-        if (iter >= 100 && (1 - std::exp(old_sum_lkl - sss_sum_lkl)) <= 0.001) { why = 2; break; }   // :265-270
+        if (iter >= conv_from + 1 && (1 - std::exp(old_sum_lkl - sss_sum_lkl)) <= 0.001) { why = 2; break; }   // :265-270
 
         // sampling, sss_postcal.cpp:289-343: one draw inside each group, then one across the groups
         const double* ll = q.h_out_l;
@@ -1152,6 +1175,120 @@ int pipsort_sss(pipsort_engine* e, int max_causal, int max_iterations, int32_t* 
         SssCur nxt;
         memset(&nxt, 0, sizeof nxt);
         nxt.k = sss_neighbour(cur, U, c, sample[grp] + lo[grp], nxt.g);  // :354
+        cur = nxt;
+        old_sum_lkl = sss_sum_lkl;
+    }
+    if (iterations) *iterations = iter;
+    if (stop_reason) *stop_reason = why;
+    return check_flags(e);
+}
+
+int pipsort_sss_sharded(pipsort_engine* e, int max_causal, int max_iterations, int32_t* iterations, int32_t* stop_reason) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    pipsort_engine::P2P& pp = e->p2p;
+    if (!pp.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
+    if (pp.world == 1) return pipsort_sss(e, max_causal, max_iterations, iterations, stop_reason);
+    const int c = max_causal, U = e->U, world = pp.world, rank = pp.rank;
+    if (c < 0 || c > e->kb) return fail(PIPSORT_E_ARG, "max_causal=%d outside [0,%d] (max_causal given at create)", c, e->kb);
+    if (U > SSS_MAX_U) return fail(PIPSORT_E_RANGE, "the search state packs union indices into 15 bits: U=%d > %d", U, SSS_MAX_U);
+    if (max_iterations < 0) return fail(PIPSORT_E_ARG, "negative iteration count");
+    CU(cudaSetDevice(e->device));
+    pipsort_engine::Sss& q = e->sss;
+    const int kmax = std::max(c, 1);
+    const long long n_max = (long long)U * std::max(c, 1) + c + U + 1;
+    if (q.n_max < n_max || q.kmax != kmax || !q.d_state) {
+        void* ps[] = {q.d_out_l, q.d_batch, q.d_upd, q.d_unseen, q.d_counter, q.d_scored, q.d_state, q.d_pos_of, q.d_total};
+        for (void* p : ps) if (p) cudaFree(p);
+        if (q.h_out_l) cudaFreeHost(q.h_out_l);
+        q.h_out_l = nullptr;
+        CU(cudaMalloc(&q.d_out_l, (size_t)(n_max + 1) * sizeof(double)));
+        CU(cudaMalloc(&q.d_batch, (size_t)(n_max + 1) * kmax * sizeof(int)));
+        CU(cudaMalloc(&q.d_upd, (size_t)(n_max + 1)));
+        CU(cudaMalloc(&q.d_unseen, (size_t)n_max * sizeof(int)));
+        CU(cudaMalloc(&q.d_counter, 2 * sizeof(int)));
+        CU(cudaMalloc(&q.d_scored, (size_t)(n_max + 1) * sizeof(double)));
+        CU(cudaMalloc(&q.d_state, (size_t)(n_max + 1)));
+        CU(cudaMalloc(&q.d_pos_of, (size_t)(n_max + 1) * sizeof(int)));
+        CU(cudaMalloc(&q.d_total, sizeof(double)));
+        CU(cudaMallocHost(&q.h_out_l, (size_t)(n_max + 2) * sizeof(double)));
+        q.n_max = n_max; q.kmax = kmax;
+    }
+    int rc = pipsort_sss_reset(e);
+    if (rc) return rc;
+    const size_t acc_len = p2p_acc_len(e), half = p2p_sss_half(e), stride = p2p_slot_len(e);
+    if ((size_t)n_max + (size_t)e->L.acc.NB > half) return fail(PIPSORT_E_ARG, "mailbox too small for this max_causal");
+    double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
+    const double cx = -0.5 * e->K + U * std::log(1.0 - e->gamma);
+
+    const int conv_from = sss_conv_from();
+    std::mt19937 gen(12345);                                             // sss_postcal.cpp:138
+    SssCur cur;
+    memset(&cur, 0, sizeof cur);
+    double old_sum_lkl = 0, sss_sum_lkl = 0;
+    int iter = 0, why = 0;
+    std::vector<double> probs;
+    for (iter = 0; iter < max_iterations; iter++) {
+        long long nz, nm, np;
+        sss_nbd_sizes(U, cur.k, c, nz, nm, np);
+        const long long n = nz + nm + np;
+        if ((rc = sss_table_reserve(e, q.count + (u64)n))) return rc;
+        // this round's exchange: epoch flag + the half of the slots it uses
+        const u64 epoch = ++q.epoch;
+        SssShard sh;
+        memset(&sh, 0, sizeof sh);
+        sh.world = world; sh.rank = rank;
+        sh.flag = (unsigned)(epoch & 0x7fffffffu) + 1u;
+        const size_t hoff = acc_len + (size_t)(epoch & 1) * half;
+        for (int p = 0; p < world; p++) {
+            if (p == rank) continue;
+            sh.peer_slot[p] = static_cast<ulonglong2*>(pp.peer_base[p]) + (size_t)rank * stride + hoff;
+            sh.my_slot[p] = reinterpret_cast<const ulonglong2*>(pp.mailbox) + (size_t)p * stride + hoff;
+        }
+        CU(cudaMemsetAsync(q.d_counter, 0, 2 * sizeof(int), e->stream));
+        const unsigned gb = (unsigned)((n + 1 + 255) / 256);
+        sss_lookup_shard_kernel<<<gb, 256, 0, e->stream>>>(q.tab, cur, U, c, n, kmax, world, rank, q.d_out_l, q.d_batch, q.d_upd,
+                                                           q.d_pos_of, q.d_state, q.d_counter);
+        e->launches++;
+        if ((rc = launch_score_batch(e, q.d_batch, 1, (n + world - 1) / world + 1, kmax, q.d_upd, q.d_scored, q.d_counter))) return rc;
+        if (n > 0) {
+            sss_push_shard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(sh, n, q.d_state, q.d_pos_of, q.d_scored);
+            sss_insert_shard_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(q.tab, cur, U, c, n, sh, q.d_state, q.d_pos_of,
+                                                                                     q.d_scored, q.d_out_l, errf);
+            e->launches += 2;
+        }
+        if (iter >= conv_from) {                                         // the running total of ALL ranks (:265-270)
+            sss_total_shard_kernel<<<1, 64, 0, e->stream>>>(e->L.acc, sh, (long long)n_max, cx, q.d_total, errf);
+            e->launches++;
+        }
+        CU(cudaGetLastError());
+        int cnt[2] = {0, 0};
+        CU(cudaMemcpyAsync(cnt, q.d_counter, sizeof cnt, cudaMemcpyDeviceToHost, e->stream));
+        if (n > 0) CU(cudaMemcpyAsync(q.h_out_l, q.d_out_l, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        if (iter >= conv_from) CU(cudaMemcpyAsync(q.h_out_l + n_max + 1, q.d_total, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        const int n_new = cnt[1];
+        if (n_new == 0) { why = 1; break; }
+        q.count += (u64)n_new;
+        if (iter >= conv_from) sss_sum_lkl = q.h_out_l[n_max + 1];
+        if (iter >= conv_from + 1 && (1 - std::exp(old_sum_lkl - sss_sum_lkl)) <= 0.001) { why = 2; break; }
+        const double* ll = q.h_out_l;
+        double weight[3] = {0.0, 0.0, 0.0};
+        long long sample[3] = {n, n, n};
+        const long long lo[3] = {0, nz, nz + nm}, hi[3] = {nz, nz + nm, n};
+        for (int g = 0; g < 3; g++) {
+            if (lo[g] == hi[g]) continue;
+            const double max_log = *std::max_element(ll + lo[g], ll + hi[g]);
+            probs.clear();
+            for (long long ii = lo[g]; ii < hi[g]; ii++) probs.push_back(std::exp(ll[ii] - max_log));
+            std::discrete_distribution<size_t> dist(probs.begin(), probs.end());
+            sample[g] = (long long)dist(gen);
+            weight[g] = std::accumulate(probs.begin(), probs.end(), 0.0);
+        }
+        std::discrete_distribution<size_t> dist({weight[0], weight[1], weight[2]});
+        const size_t grp = dist(gen);
+        SssCur nxt;
+        memset(&nxt, 0, sizeof nxt);
+        nxt.k = sss_neighbour(cur, U, c, sample[grp] + lo[grp], nxt.g);
         cur = nxt;
         old_sum_lkl = sss_sum_lkl;
     }
@@ -1454,8 +1591,7 @@ int pipsort_merge(pipsort_engine* dst, pipsort_engine* src) {
 static int shard_by_types(const std::vector<int>& types, int c, int parts, uint64_t* bounds);
 
 // ---- peer-memory combine -----------------------------------------------------------------------------------
-// mailbox layout: world slots of slot_len 16-byte elements (slot_len = bins_len rounded up to 16) | 8 control words
-static size_t p2p_slot_len(const pipsort_engine* e) { return (e->bins_len + 15) & ~(size_t)15; }
+
 
 int pipsort_p2p_export(pipsort_engine* e, int world, void* handle) {
     if (!e || !handle) return fail(PIPSORT_E_ARG, "null argument");

@@ -152,6 +152,157 @@ sss_insert_kernel(SssTable tab, const int* __restrict__ batch, int kmax, const d
     sss_put(tab, lo, hi, v);
 }
 
+// ---- the same search with the neighbourhood split over several GPUs (one process per GPU, sss_postcal.cpp:223-255 is the
+// loop being split) -------------------------------------------------------------------------------------------------------
+// Every rank runs the whole search in lockstep on a REPLICATED explored-configuration table (same seed, same values, hence
+// the same trajectory); of every round's unseen neighbours rank r expands + scores + accumulates those with
+// neighbour index i = r (mod world); the max-|l| values travel to every peer through the mailboxes of p2p.cuh (each double
+// as two self-validating words, written straight into the peer's memory over NVLink); the accumulators stay rank-partial
+// until they are combined (pipsort_p2p_reduce_to_root / all-reduce) at the end.
+struct SssShard {
+    int world, rank;
+    unsigned flag;                       // this round's epoch (low 32 bits), never 0
+    ulonglong2* peer_slot[16];           // [p]: where THIS rank's values go in peer p's mailbox (nullptr for p == rank)
+    const ulonglong2* my_slot[16];       // [p]: where peer p's values arrive in this rank's mailbox
+};
+
+// thread i < n: neighbour i; thread n: the current configuration (scored by rank 0 when unseen).  out_l[i] gets the stored
+// value of a seen neighbour; unseen ones are flagged (state[i] = 1) on every rank and appended to THIS rank's batch when
+// i = rank (mod world) (pos_of[i] = row of the batch).
+__global__ void __launch_bounds__(256)
+sss_lookup_shard_kernel(SssTable tab, SssCur cur, int U, int c, long long n, int kmax, int world, int rank, double* __restrict__ out_l,
+                        int* __restrict__ batch, unsigned char* __restrict__ upd, int* __restrict__ pos_of,
+                        unsigned char* __restrict__ state, int* __restrict__ counter /* [0] own batch rows, [1] unseen in total */) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    int cfg[KMAX];
+    int kk;
+    if (i == n) { kk = cur.k; for (int j = 0; j < kk; j++) cfg[j] = cur.g[j]; }
+    else kk = sss_neighbour(cur, U, c, i, cfg);
+    u64 lo, hi;
+    sss_key(cfg, kk, lo, hi);
+    double v = 0.0;
+    const bool found = sss_find(tab, lo, hi, v);
+    int row = -1;
+    if (i == n) {
+        // the current configuration is re-scored only when unseen, by rank 0; the other ranks keep row 0 as a no-op
+        row = 0;
+        upd[0] = (!found && rank == 0) ? 1 : 0;
+        if (rank != 0) kk = -1;                                  // all -1: scored as the null configuration WITHOUT updates
+    } else {
+        state[i] = found ? 0 : 1;
+        if (found) { out_l[i] = v; return; }
+        atomicAdd(counter + 1, 1);
+        if ((int)(i % world) != rank) return;
+        const int pos = atomicAdd(counter, 1);
+        pos_of[i] = 1 + pos;
+        row = 1 + pos;
+        upd[row] = 1;
+    }
+    for (int j = 0; j < kmax; j++) batch[(size_t)row * kmax + j] = j < kk ? cfg[j] : -1;
+}
+
+// thread i < n: an unseen neighbour scored by this rank sends its value to every peer
+__global__ void __launch_bounds__(256)
+sss_push_shard_kernel(SssShard sh, long long n, const unsigned char* __restrict__ state, const int* __restrict__ pos_of,
+                      const double* __restrict__ scored) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !state[i] || (int)(i % sh.world) != sh.rank) return;
+    const u64 b = (u64)__double_as_longlong(scored[pos_of[i]]);
+    const u64 f = (u64)sh.flag << 32;
+    const ulonglong2 w = make_ulonglong2((b & 0xffffffffull) | f, (b >> 32) | f);
+    for (int p = 0; p < sh.world; p++)
+        if (p != sh.rank) sh.peer_slot[p][i] = w;
+}
+
+// thread i < n: every unseen neighbour enters the (replicated) table on every rank, with the value its owner computed
+__global__ void __launch_bounds__(256)
+sss_insert_shard_kernel(SssTable tab, SssCur cur, int U, int c, long long n, SssShard sh, const unsigned char* __restrict__ state,
+                        const int* __restrict__ pos_of, const double* __restrict__ scored, double* __restrict__ out_l,
+                        double* __restrict__ err_flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !state[i]) return;
+    const int owner = (int)(i % sh.world);
+    double v;
+    if (owner == sh.rank) {
+        v = scored[pos_of[i]];
+    } else {
+        const volatile ulonglong2* src = sh.my_slot[owner] + i;
+        u64 w0, w1;
+        const long long t0 = clock64();
+        bool ok = true;
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src));
+            if ((unsigned)(w0 >> 32) == sh.flag && (unsigned)(w1 >> 32) == sh.flag) break;
+            if (clock64() - t0 > 120000000000ll) { ok = false; break; }
+            __nanosleep(64);
+        }
+        if (!ok) { atomicAdd(err_flag, 1.0); return; }
+        v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+    int cfg[KMAX];
+    const int kk = sss_neighbour(cur, U, c, i, cfg);
+    u64 lo, hi;
+    sss_key(cfg, kk, lo, hi);
+    out_l[i] = v;
+    sss_put(tab, lo, hi, v);
+}
+
+// The running total (sss_sum_lkl, consulted by the convergence rule from round 100 on, sss_postcal.cpp:265-270) is the sum of
+// the ranks' partial totals: every rank sends the bins of its total to every peer and adds all of them in rank order, so
+// that all ranks see bit-identical sums and take the same branch.  One block.
+__global__ void __launch_bounds__(64)
+sss_total_shard_kernel(AccDev acc, SssShard sh, long long off, double cx, double* __restrict__ out_total, double* __restrict__ err_flag) {
+    const int b = threadIdx.x;
+    const int NB = acc.NB;
+    const u64 f = (u64)sh.flag << 32;
+    for (int t = b; t < NB; t += 64) {
+        const u64 bits = (u64)__double_as_longlong(bin_ptr(acc, SCAL, S_TOTAL)[(size_t)t * acc.Upad]);
+        const ulonglong2 w = make_ulonglong2((bits & 0xffffffffull) | f, (bits >> 32) | f);
+        for (int p = 0; p < sh.world; p++)
+            if (p != sh.rank) sh.peer_slot[p][off + t] = w;
+    }
+    // top three non-empty bins of the summed total (NB <= 64 * k handled by a serial tail in thread 0: NB is ~10-100)
+    __shared__ double tot[512];
+    for (int t = b; t < NB && t < 512; t += 64) {
+        double v = 0.0;
+        for (int p = 0; p < sh.world; p++) {
+            double x;
+            if (p == sh.rank) {
+                x = bin_ptr(acc, SCAL, S_TOTAL)[(size_t)t * acc.Upad];
+            } else {
+                const volatile ulonglong2* src = sh.my_slot[p] + off + t;
+                u64 w0, w1;
+                const long long t0 = clock64();
+                for (;;) {
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src));
+                    if ((unsigned)(w0 >> 32) == sh.flag && (unsigned)(w1 >> 32) == sh.flag) break;
+                    if (clock64() - t0 > 120000000000ll) { atomicAdd(err_flag, 1.0); break; }
+                    __nanosleep(64);
+                }
+                x = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            }
+            v += x;
+        }
+        tot[t] = v;
+    }
+    __syncthreads();
+    if (b == 0) {
+        int top = -1;
+        for (int t = 0; t < NB && t < 512; t++) if (tot[t] > 0.0) top = t;
+        double r = 0.0;
+        if (top >= 0) {
+            double M = tot[top];
+            if (top > 0) M += tot[top - 1] * 0x1p-512;
+            if (top > 1) M += (tot[top - 2] * 0x1p-512) * 0x1p-512;
+            const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+            const double nn = (double)(512 * top - acc.bias);
+            r = (nn * LN2_HI + (log(M) + nn * LN2_LO)) + cx;
+        }
+        *out_total = r;
+    }
+}
+
 __global__ void __launch_bounds__(256) sss_rehash_kernel(SssTable from, SssTable to) {
     const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s > from.mask) return;

@@ -171,6 +171,21 @@ def score_union_configs_sharded(engine, idx, make_updates=None, group=None):
     return np.concatenate([recv[r, :b[r + 1] - b[r]] for r in range(world)])
 
 
+def sss_sharded(engine, c=None, max_iterations=1000, group=None, root=0):
+    """sss_computeTotalLikelihood (sss_postcal.cpp:102-380) with every round's neighbourhood split over the ranks
+    (pipsort_sss_sharded; connect_p2p first).  Returns (Results on the root / None elsewhere, iterations, stop_reason)."""
+    world, rank = world_and_rank(group)
+    engine.reset()
+    if world == 1:
+        return engine.sss(c, max_iterations)
+    it, why = engine.sss_sharded(c, max_iterations)
+    engine.p2p_reduce_to_root()
+    if rank != root:
+        engine.sync()
+        return None, it, why
+    return engine.read(), it, why
+
+
 def read_sharded(engine, group=None):
     """Results of rank-partial accumulators (after score_union_configs_sharded): all-reduce a COPY of the store so the
     partial sums can keep accumulating, finalize from the copy, restore."""

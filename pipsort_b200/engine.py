@@ -83,6 +83,7 @@ def lib():
         L.pipsort_score_given_configs_device.argtypes = [vp, vp, C.c_int64, i32]
         L.pipsort_sss.argtypes = [vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pipsort_sss_reset.argtypes = [vp]
+        L.pipsort_sss_sharded.argtypes = [vp, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.pipsort_read_accumulators.argtypes = [vp, C.POINTER(_Outputs)]
         L.pipsort_finalize.argtypes = [vp]
         L.pipsort_finalize_reset.argtypes = [vp]
@@ -271,6 +272,15 @@ class Engine:
         self.reset()
         _check(lib().pipsort_sss(self._h, int(c), int(max_iterations), C.byref(it), C.byref(why)))
         return self.read(), int(it.value), int(why.value)
+
+    def sss_sharded(self, c=None, max_iterations=1000):
+        """pipsort_sss_sharded: the search with every neighbourhood split over the ranks of the p2p group (call on every
+        rank after p2p_connect, on fresh accumulators).  The accumulators stay rank-partial: follow with
+        p2p_reduce_to_root() and read() on the root.  Returns (iterations, stop_reason)."""
+        c = self.max_causal if c is None else c
+        it, why = C.c_int32(), C.c_int32()
+        _check(lib().pipsort_sss_sharded(self._h, int(c), int(max_iterations), C.byref(it), C.byref(why)))
+        return int(it.value), int(why.value)
 
     def read(self) -> Results:
         return self._read(lib().pipsort_read_accumulators)

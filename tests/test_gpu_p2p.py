@@ -101,3 +101,65 @@ def test_two_ranks_nccl_allreduce_without_stream_binding():
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_nccl_worker, args=(2, os.path.join(tmp, "init"), tmp), nprocs=2, join=True)
         assert os.path.exists(os.path.join(tmp, "ok0")) and os.path.exists(os.path.join(tmp, "ok1"))
+
+
+def _sss_worker(rank, world, initfile, outdir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pipsort_b200 import distributed as D
+    from pipsort_b200 import synth
+    from oracle import oracle as O
+    from conftest import golden, args_to_params, synth_as_oracle_locus
+    dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
+    try:
+        dev = rank % torch.cuda.device_count()
+        torch.cuda.set_device(dev)
+        # the reference's own `-q 1` dumps: same trajectory (round count, stop reason), same accumulators
+        for name in ("small_sss_c3_p075", "example_sss_c2_p025"):
+            g = golden(name)
+            prm = args_to_params(g["args"])
+            L = oracle_locus(g["dataset"], p=prm["p"], gamma=prm["gamma"], s=prm["s"], t=prm["t"])
+            want = O.sss(L, prm["c"])
+            with engine_for(L, prm["c"], device=dev) as e:
+                assert D.connect_p2p(e)
+                for rep in range(2):                               # a second search on the same engine: epochs keep counting
+                    r, iters, why = D.sss_sharded(e, prm["c"])
+                    assert iters == want.extra["n_iter"]
+                    assert (why == 1) == any("hit break condition" in f for f in g["stdout_flags"])
+                    if rank == 0:
+                        assert_results_match(r, g)
+                    else:
+                        assert r is None
+        # the longest trajectory we found (9 rounds; 12+12 SNPs), against the oracle ...
+        SL = synth.make_locus(12, overlap=0.7, seed=18)
+        want = O.sss(synth_as_oracle_locus(SL), 3)
+        assert want.extra["n_iter"] == 9
+        with engine_for(SL, 3, device=dev) as e:
+            assert D.connect_p2p(e)
+            r, iters, why = D.sss_sharded(e, 3)
+            assert iters == 9 and why == 1
+            if rank == 0:
+                assert_results_match(r, want)
+            # ... and with the convergence rule switched on from round 2 (the reference starts at round 100, which no search
+            # we know reaches): the running total every rank consults is the sum over ALL ranks' partial accumulators, so
+            # the split search must stop in the same round with the same accumulators as the search on one GPU
+            os.environ["PIPSORT_SSS_CONV_FROM"] = "2"
+            try:
+                one, it1, why1 = e.sss(3)
+                r, iters, why = D.sss_sharded(e, 3)
+            finally:
+                os.environ.pop("PIPSORT_SSS_CONV_FROM", None)
+            assert (iters, why) == (it1, why1) and why1 == 2 and it1 < 9
+            if rank == 0:
+                assert_results_match(r, one, rtol=1e-12)
+        open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sss_neighbourhoods_split_over_ranks(world):
+    """pipsort_sss_sharded: every rank scores its share of each round's unseen neighbours, the values travel through the
+    peer-memory mailboxes, the replicated search state follows the reference's trajectory on every rank."""
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_sss_worker, args=(world, os.path.join(tmp, "init"), tmp), nprocs=world, join=True)
+        assert all(os.path.exists(os.path.join(tmp, f"ok{r}")) for r in range(world))
