@@ -241,6 +241,10 @@ int pipsort_p2p_reduce_to_root(pipsort_engine* e);
 /* The same, and a NON-root rank's accumulators are left empty by the very kernel that sends them (the root's are emptied
  * by pipsort_finalize_reset): a repeated pass needs no pipsort_reset on any rank.                                 */
 int pipsort_p2p_reduce_to_root_reset(pipsort_engine* e);
+/* The whole tail of a repeatable multi-GPU pass in ONE launch per rank: a non-root rank sends its store (and empties it); the
+ * root sums its own store and the peers' slots straight into the finalize (bins -> results; nothing is written back but
+ * zeros) -- the results are then fetched on the root with pipsort_fetch_results.  Stream-ordered, asynchronous.            */
+int pipsort_p2p_combine_finalize(pipsort_engine* e);
 
 /* Split [0,total) into `parts` contiguous rank ranges of roughly equal work (expanded configurations
  * weighted); bounds receives parts+1 values.                                                      */

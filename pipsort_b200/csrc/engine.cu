@@ -202,6 +202,61 @@ __global__ void __launch_bounds__(FIN_WARPS * 32) finalize_kernel(AccDev acc, in
     res[3 + (size_t)lane * U + g] = xlog_or_zero(mine, lane < 3 ? cx : cy);
 }
 
+// The root's half of the multi-GPU combine step fused with the finalize (accumulators of at most 32 bins): lane b of the warp
+// of a SNP takes bin b of the SNP's five accumulators from the root's own store AND from every peer's mailbox slot (polling
+// each element until it carries this epoch's flag, p2p.cuh), so the sum over the GPUs never goes back to memory; the root's
+// store is left empty.  The last block posts `consumed` to the peers.  Replaces p2p_merge_kernel + finalize_kernel.
+__global__ void __launch_bounds__(FIN_WARPS * 32)
+finalize_merge_kernel(AccDev acc, int U, double cx, double cy, double* __restrict__ res, const ulonglong2* slots, size_t slot_stride,
+                      size_t bins_len, u64* __restrict__ my_ctrl, P2PPeers peers, int my_rank, unsigned* __restrict__ done,
+                      double* __restrict__ err_flag) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const u64 epoch = *(volatile u64*)(my_ctrl + 2) + 1;           // stable until the last block bumps it below
+    const u64 flag = epoch & 0xffffffffull;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * FIN_WARPS + (threadIdx.x >> 5);
+    bool ok = true;
+    auto take = [&](size_t idx) -> double {                        // element idx of the store, summed over all GPUs; own copy cleared
+        double v = acc.bins[idx];
+        if (v != 0.0) acc.bins[idx] = 0.0;
+        for (int r = 0; r < peers.world; r++)
+            if (r != my_rank) v += p2p_take(slots + (size_t)r * slot_stride + idx, flag, ok);
+        return v;
+    };
+    if (blockIdx.x == 0 && threadIdx.x < NCOUNTER) res[3 + (size_t)5 * U + threadIdx.x] = take(bins_len - NCOUNTER + threadIdx.x);
+    if (w < 3) {
+        const double v = lane < acc.NB ? take(((size_t)SCAL * acc.NB + lane) * acc.Upad + w) : 0.0;
+        const XAcc x = bins_from_lanes(v, acc.bias);
+        if (lane == 0) res[w] = xlog_or_zero(x, cx);
+    } else if (w - 3 < U) {
+        const int g = w - 3;
+        double v[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[k] = lane < acc.NB ? take(((size_t)k * acc.NB + lane) * acc.Upad + g) : 0.0;
+        const XAcc x1 = bins_from_lanes(v[X1], acc.bias), x2 = bins_from_lanes(v[X2], acc.bias), x3 = bins_from_lanes(v[X3], acc.bias);
+        const XAcc ys = bins_from_lanes(v[YS], acc.bias), yn = bins_from_lanes(v[YN], acc.bias);
+        if (lane < 5) {
+            XAcc p0 = x1, p1 = x2;
+            xmerge(p0, x3);
+            xmerge(p1, x3);
+            const XAcc mine = lane == 0 ? p0 : (lane == 1 ? p1 : (lane == 2 ? x3 : (lane == 3 ? ys : yn)));
+            res[3 + (size_t)lane * U + g] = xlog_or_zero(mine, lane < 3 ? cx : cy);
+        }
+    }
+    if (!ok) atomicAdd(err_flag, 1.0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned d = atomicAdd(done, 1u);
+        if (d == gridDim.x - 1) {                    // every block has read the slots: the peers may overwrite them
+            *done = 0;
+            my_ctrl[2] = epoch;
+            __threadfence_system();
+            for (int r = 0; r < peers.world; r++)
+                if (r != my_rank) *(volatile u64*)(peers.ctrl[r] + 1) = epoch;
+        }
+    }
+}
+
 __global__ void add_bins_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] += src[i];
@@ -1649,6 +1704,38 @@ int pipsort_p2p_reduce_to_root_reset(pipsort_engine* e) {
     if (!e) return fail(PIPSORT_E_ARG, "null engine");
     return p2p_reduce_impl(e, true);
 }
+static int finalize_launch(pipsort_engine* e, bool clear);
+int pipsort_p2p_combine_finalize(pipsort_engine* e) {
+    if (!e) return fail(PIPSORT_E_ARG, "null engine");
+    pipsort_engine::P2P& q = e->p2p;
+    if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
+    if (q.world == 1) return finalize_launch(e, true);
+    if (q.rank != q.root) return p2p_reduce_impl(e, true);
+    if (e->L.acc.NB > 32) {                          // many bins: merge into the store, then the scanning finalize
+        int rc = p2p_reduce_impl(e, true);
+        return rc ? rc : finalize_launch(e, true);
+    }
+    CU(cudaSetDevice(e->device));
+    const int U = e->U;
+    const double cy = -0.5 * e->K, cx = cy + U * std::log(1.0 - e->gamma);
+    static const bool no_pdl = getenv("PIPSORT_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((U + 3 + FIN_WARPS - 1) / FIN_WARPS);
+    cfg.blockDim = dim3(FIN_WARPS * 32);
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
+    CU(cudaLaunchKernelEx(&cfg, finalize_merge_kernel, e->L.acc, U, cx, cy, e->d_res, reinterpret_cast<const ulonglong2*>(q.mailbox),
+                          p2p_slot_len(e), e->bins_len, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf));
+    e->launches++;
+    return 0;
+}
+
 static int p2p_reduce_impl(pipsort_engine* e, bool clear_sender) {
     pipsort_engine::P2P& q = e->p2p;
     if (!q.connected) return fail(PIPSORT_E_ARG, "pipsort_p2p_connect has not been called");
@@ -1657,15 +1744,25 @@ static int p2p_reduce_impl(pipsort_engine* e, bool clear_sender) {
     const size_t n = e->bins_len, slot = p2p_slot_len(e);
     const unsigned blocks = (unsigned)std::min<size_t>((n + 511) / 512, (size_t)e->sm_count * 2);
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
+    static const bool no_pdl = getenv("PIPSORT_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = e->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = no_pdl ? 0 : 1;
     if (q.rank != q.root) {
-        p2p_push_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, n, static_cast<ulonglong2*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
-                                                       q.peers.ctrl[q.rank], q.d_done, errf, clear_sender ? 1 : 0);
+        CU(cudaLaunchKernelEx(&cfg, p2p_push_kernel, e->L.acc.bins, n, static_cast<ulonglong2*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
+                              q.peers.ctrl[q.rank], q.d_done, errf, clear_sender ? 1 : 0));
     } else {
-        p2p_merge_kernel<<<blocks, 256, 0, e->stream>>>(e->L.acc.bins, reinterpret_cast<const ulonglong2*>(q.mailbox), n, slot,
-                                                        q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf);
+        CU(cudaLaunchKernelEx(&cfg, p2p_merge_kernel, e->L.acc.bins, reinterpret_cast<const ulonglong2*>(q.mailbox), n, slot,
+                              q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf));
     }
     e->launches++;
-    CU(cudaGetLastError());
     return 0;
 }
 

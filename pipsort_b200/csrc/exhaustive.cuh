@@ -101,25 +101,25 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
     auto plan = std::make_shared<std::vector<ExhChunkDesc>>();
     const double steps = (have3 ? exh_class_steps(U, 3, p3.a_lo, p3.a_hi) : 0.0) + (have2 ? exh_class_steps(U, 2, 0, 0) : 0.0);
     // Granularity (measured on B200, scripts/sweep_chunks.py).  avg = modelled cost per resident warp.
-    //   avg <= 12      : chunks of 12 steps -- fewer chunks than warps, every set-up paid once;
+    //   avg <= 3       : chunks of 3 steps -- fewer chunks than warps (a 1/8 shard of a small locus, a c = 2 run);
     //   avg <= 64      : ONE chunk per resident warp, all of the same cost (a static, even deal: the kernel time of a small
     //                    locus is the time of its longest chunk);
     //   beyond         : ~avg / 32 (at most 12) chunks per resident warp, balanced by the work queue.
     double target = key.forced;
     if (!(target > 0.0)) {
         double avg = 1.15 * steps / key.slots;
-        for (int pass = 0; pass < 2 && avg > 12.0 && avg <= 64.0; pass++) {     // set-up costs depend on the cuts: one refinement
+        for (int pass = 0; pass < 2 && avg > 3.0 && avg <= 64.0; pass++) {     // set-up costs depend on the cuts: one refinement
             plan->clear();
             double tot = 0.0;
             if (have3) tot += exh_plan_class(U, 3, p3.a_lo, p3.a_hi, avg, cs, *plan);
             if (have2) tot += exh_plan_class(U, 2, 0, 0, avg, cs, *plan);
             avg = 1.01 * tot / key.slots;
         }
-        if (avg <= 12.0) target = 12.0;
+        if (avg <= 3.0) target = 3.0;
         else if (avg <= 64.0) target = avg;
         else target = avg / std::min(12.0, std::floor(avg / 32.0));
     }
-    const bool one_round = !(key.forced > 0.0) && target > 12.0 && target <= 64.0 * 1.02;
+    const bool one_round = !(key.forced > 0.0) && target > 3.0 && target <= 64.0 * 1.02;
     for (int tries = 0; tries < 6; tries++) {
         plan->clear();
         if (have3) exh_plan_class(U, 3, p3.a_lo, p3.a_hi, target, cs, *plan);

@@ -39,11 +39,27 @@ __device__ inline bool p2p_spin_ge(const volatile u64* p, u64 target) {
     return true;
 }
 
+// one element of a peer's slot: spins until both words carry this epoch's flag (8-byte stores are single-copy atomic)
+__device__ __forceinline__ double p2p_take(const ulonglong2* src, u64 flag, bool& ok) {
+    u64 w0, w1;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src));
+        if ((w0 >> 32) == flag && (w1 >> 32) == flag) break;
+        if (clock64() - t0 > P2P_SPIN_CYCLES) { ok = false; break; }
+        __nanosleep(32);
+    }
+    return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
+
 __global__ void __launch_bounds__(256)
 p2p_push_kernel(double* __restrict__ store, size_t n, ulonglong2* __restrict__ my_slot_at_root, u64* __restrict__ my_ctrl,
                 unsigned* __restrict__ done, double* __restrict__ err_flag, int clear) {
     __shared__ int ok;
     __shared__ u64 epoch_s;
+    // (launched with programmatic stream serialization: resident early, but the store is final only when the kernel
+    // before this one in the stream has completed)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // the epoch lives in device memory (control word 2, bumped by the last block) so that the launch has no per-step
     // argument and can be replayed from a CUDA graph
     if (threadIdx.x == 0) {
@@ -71,6 +87,7 @@ p2p_push_kernel(double* __restrict__ store, size_t n, ulonglong2* __restrict__ m
 __global__ void __launch_bounds__(256)
 p2p_merge_kernel(double* __restrict__ store, const ulonglong2* slots, size_t n, size_t slot_stride, u64* __restrict__ my_ctrl,
                  P2PPeers peers, int my_rank, unsigned* __restrict__ done, double* __restrict__ err_flag) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const u64 epoch = *(volatile u64*)(my_ctrl + 2) + 1;           // stable until the last block bumps it below
     const u64 flag = epoch & 0xffffffffull;
     bool ok = true;

@@ -115,8 +115,8 @@ def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allre
 def pass_exhaustive_sharded(engine, c, bounds, collective="p2p", root=0, group=None):
     """One REPEATABLE pass on accumulators that are already empty (a fresh engine, or the previous pass of this function):
     this rank's share of computeTotalLikelihood, the combine step and the finalize, with every reset folded into the
-    kernels that read the store last -- the non-root ranks' push empties their stores, the root's finalize empties its
-    own.  Two launches on the root (three with the merge), two on the others; asynchronous; the root's results are then
+    kernels that read the store last -- the non-root ranks' push empties their stores, the root's finalize (which also
+    sums the peers' stores, straight from their mailbox slots) empties its own.  Two launches on every rank; asynchronous; the root's results are then
     read with engine.fetch().  collective="allreduce" keeps an explicit reset (NCCL reads and writes the store itself)."""
     world, rank = world_and_rank(group)
     if world == 1:
@@ -125,9 +125,7 @@ def pass_exhaustive_sharded(engine, c, bounds, collective="p2p", root=0, group=N
         return
     if collective == "p2p":
         engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])
-        engine.p2p_reduce_to_root(reset_sender=True)
-        if rank == root:
-            engine.finalize(reset=True)
+        engine.p2p_combine_finalize()         # non-root: send + empty; root: sum over the GPUs inside the finalize
         return
     _order_with_torch(engine)
     engine.run_exhaustive(c, bounds[rank], bounds[rank + 1])

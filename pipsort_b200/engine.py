@@ -103,6 +103,7 @@ def lib():
         L.pipsort_p2p_connect.argtypes = [vp, C.c_char_p, i32, i32, i32]
         L.pipsort_p2p_reduce_to_root.argtypes = [vp]
         L.pipsort_p2p_reduce_to_root_reset.argtypes = [vp]
+        L.pipsort_p2p_combine_finalize.argtypes = [vp]
         L.pipsort_shard_ranks_for_map.argtypes = [C.POINTER(C.c_int32), C.c_int32, i32, i32, C.c_uint32, C.POINTER(u64)]
         L.pipsort_stream.argtypes = [vp]
         L.pipsort_stream.restype = vp
@@ -362,6 +363,10 @@ class Engine:
 
     def p2p_reduce_to_root(self, reset_sender=False):
         _check(lib().pipsort_p2p_reduce_to_root_reset(self._h) if reset_sender else lib().pipsort_p2p_reduce_to_root(self._h))
+
+    def p2p_combine_finalize(self):
+        """Tail of a repeatable multi-GPU pass, one launch per rank (pipsort_p2p_combine_finalize); fetch() on the root."""
+        _check(lib().pipsort_p2p_combine_finalize(self._h))
 
     def shard_ranks(self, c, parts):
         b = (C.c_uint64 * (parts + 1))()
