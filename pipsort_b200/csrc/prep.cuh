@@ -39,7 +39,10 @@ struct CusolverApi {
     decltype(&cusolverDnDgetrf) Dgetrf = nullptr;
     decltype(&cusolverDnDsyevd_bufferSize) Dsyevd_bufferSize = nullptr;
     decltype(&cusolverDnDsyevd) Dsyevd = nullptr;
-    bool ok = false;
+    decltype(&cusolverDnDpotrf_bufferSize) Dpotrf_bufferSize = nullptr;
+    decltype(&cusolverDnDpotrf) Dpotrf = nullptr;
+    decltype(&cusolverDnDpotrs) Dpotrs = nullptr;
+    bool ok = false, chol = false;
 };
 
 inline const CusolverApi& cusolver_api() {
@@ -59,8 +62,11 @@ inline const CusolverApi& cusolver_api() {
         PIPSORT_SYM(Dgetrf, "cusolverDnDgetrf");
         PIPSORT_SYM(Dsyevd_bufferSize, "cusolverDnDsyevd_bufferSize");
         PIPSORT_SYM(Dsyevd, "cusolverDnDsyevd");
-#undef PIPSORT_SYM
+        PIPSORT_SYM(Dpotrf_bufferSize, "cusolverDnDpotrf_bufferSize");
+        PIPSORT_SYM(Dpotrf, "cusolverDnDpotrf");
+        PIPSORT_SYM(Dpotrs, "cusolverDnDpotrs");
         a.ok = a.Create && a.Destroy && a.SetStream && a.Dgetrf_bufferSize && a.Dgetrf && a.Dsyevd_bufferSize && a.Dsyevd;
+        a.chol = a.Dpotrf_bufferSize && a.Dpotrf && a.Dpotrs;
         return a;
     }();
     return api;
@@ -146,6 +152,20 @@ __global__ void __launch_bounds__(256) prep_k_sum_kernel(const double* __restric
     if (threadIdx.x == 0) { out[0] = red[0]; out[1] = mn[0]; out[2] = (double)neg[0]; }
 }
 
+// out[0] = a . b in a fixed order (one block)
+__global__ void __launch_bounds__(256) prep_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int n, double* __restrict__ out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int r = threadIdx.x; r < n; r += 256) s = fma(a[r], b[r], s);
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
 // A += 2 |w_i| q_i q_i^T for every negative eigenvalue (model.h:227 takes |Omega|)
 __global__ void prep_abs_fix_kernel(double* __restrict__ A, const double* __restrict__ Q, const double* __restrict__ w, int n) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -155,6 +175,53 @@ __global__ void prep_abs_fix_kernel(double* __restrict__ A, const double* __rest
     for (int i = 0; i < n && w[i] < 0.0; i++)   // Dsyevd returns the eigenvalues in ascending order
         acc = fma(-2.0 * w[i] * Q[(size_t)i * n + r], Q[(size_t)i * n + c], acc);
     A[idx] += acc;
+}
+
+// ---- certificates that spare most LU factorizations of the PSD loop -----------------------------------------------------
+// util.cpp:204-221 keeps adding 0.01 while the LU determinant -- the product of the pivots in index order -- is not > 0.  For
+// thousands of SNPs the product UNDERFLOWS (every pivot < 1), so the loop runs dozens of times although the matrix has long
+// been positive definite (it ends when the running product gets stuck at the smallest denormal: every remaining pivot
+// > 0.5).  Whether a shift fails can be decided without its LU:
+//   * the shifted matrix is symmetric and has a Cholesky factor L (3 ms instead of 24 ms at 5000 SNPs);
+//   * every column of L has its largest entry on the diagonal  =>  partial pivoting never swaps rows (the candidates of
+//     column k are l_ik l_kk), so the LU pivots ARE l_kk^2 up to rounding;
+//   * the running product of the pivots INFLATED by 1e-8 (far more than that rounding) still reaches exactly 0  =>  so
+//     does the reference's (rounded multiplication is monotone in each factor).
+// A shift without such a certificate gets its real LU, in particular the first one that might pass.
+__global__ void prep_is_symmetric_kernel(const double* __restrict__ A, int n, int* __restrict__ asym) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const size_t i = idx / n, j = idx - i * n;
+    if (j > i && A[idx] != A[j * n + i]) *asym = 1;
+}
+
+// dst = src + shift I (no transpose needed: only called for symmetric matrices)
+__global__ void prep_shift_plain_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, double shift) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const size_t i = idx / n, j = idx - i * n;
+    dst[idx] = src[idx] + (i == j ? shift : 0.0);
+}
+
+// Lf: potrf output, factor in the UPPER triangle of the column-major view (U^T U, U[k][i] at Lf[i * n + k], i >= k), i.e. row k
+// of U = column k of L.  One block per k: flag[0] = 1 when some |u_ki| is not clearly below u_kk.
+__global__ void __launch_bounds__(256) prep_chol_colmax_kernel(const double* __restrict__ Lf, int n, int* __restrict__ flag) {
+    const int k = blockIdx.x;
+    const double d = Lf[(size_t)k * n + k] * (1.0 - 1e-8);
+    bool bad = !(d > 0.0);
+    for (int i = k + 1 + threadIdx.x; i < n; i += 256) bad |= !(fabs(Lf[(size_t)i * n + k]) < d);
+    if (bad) *flag = 1;
+}
+
+// out[0] = the running product of the inflated pivots u_kk^2 (1 + 1e-8) in index order (one thread, like gsl_linalg_LU_det)
+__global__ void prep_chol_product_kernel(const double* __restrict__ Lf, int n, double* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double d = 1.0;
+    for (int i = 0; i < n; i++) {
+        const double u = Lf[(size_t)i * n + i];
+        d *= (u * u) * (1.0 + 1e-8);
+    }
+    out[0] = d;
 }
 
 struct PrepResult {
@@ -211,28 +278,91 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
     if (trace) fprintf(stderr, "[prep] n=%d: handle + buffers %.1f ms\n", n, tms(t_enter, t_setup));
     // 1. makeSigmaPositiveSemiDefinite
     double addDiag = 0.0;
-    int iters = 0;
-    for (;;) {
-        prep_shift_copy_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, stream>>>(dA, dW, n, addDiag);
-        PREP_CS(cs.Dgetrf(h, n, n, dW, n, dwork, dipiv, dinfo));
-        prep_lu_det_kernel<<<1, 32, 0, stream>>>(dW, dipiv, n, dscal);
-        *launches += 2;
-        double det = 0.0;
-        PREP_CU(cudaMemcpyAsync(&det, dscal, sizeof det, cudaMemcpyDeviceToHost, stream));
+    int iters = 0, n_lu = 0, n_cert = 0;
+    static const int chol_min = [] { const char* v = getenv("PIPSORT_PREP_CHOL_MIN"); return v ? atoi(v) : 1024; }();
+    bool use_chol = cs.chol && n >= chol_min;
+    int lw_ch = 0;
+    int* dflag = nullptr;
+    if (use_chol) {
+        PREP_CU(cudaMallocAsync(&dflag, 2 * sizeof(int), stream));
+        PREP_CU(cudaMemsetAsync(dflag, 0, 2 * sizeof(int), stream));
+        prep_is_symmetric_kernel<<<blocks, 256, 0, stream>>>(dA, n, dflag);
+        int asym = 0;
+        PREP_CU(cudaMemcpyAsync(&asym, dflag, sizeof asym, cudaMemcpyDeviceToHost, stream));
         PREP_CU(cudaStreamSynchronize(stream));
+        if (asym) use_chol = false;                 // the reference factorises the matrix as read: no certificate for those
+        else {
+            PREP_CS(cs.Dpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, n, dW, n, &lw_ch));
+            if (lw_ch > std::max(std::max(lw_lu, lw_ev), 1)) use_chol = false;   // (never: potrf needs less than getrf / syevd)
+        }
+    }
+    auto cleanup2 = [&]() { if (dflag) cudaFreeAsync(dflag, stream); };
+    for (;;) {
+        bool certified = false;
+        if (use_chol) {                             // can this shift be shown to fail without its LU?
+            PREP_CU(cudaMemsetAsync(dflag, 0, 2 * sizeof(int), stream));
+            prep_shift_plain_kernel<<<blocks, 256, 0, stream>>>(dA, dW, n, addDiag);
+            PREP_CS(cs.Dpotrf(h, CUBLAS_FILL_MODE_UPPER, n, dW, n, dwork, lw_ch, dinfo));
+            prep_chol_colmax_kernel<<<n, 256, 0, stream>>>(dW, n, dflag);
+            prep_chol_product_kernel<<<1, 32, 0, stream>>>(dW, n, dscal);
+            *launches += 3;
+            int hinfo = 0, hflag[2] = {0, 0};
+            double prod = 1.0;
+            PREP_CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof hinfo, cudaMemcpyDeviceToHost, stream));
+            PREP_CU(cudaMemcpyAsync(hflag, dflag, sizeof hflag, cudaMemcpyDeviceToHost, stream));
+            PREP_CU(cudaMemcpyAsync(&prod, dscal, sizeof prod, cudaMemcpyDeviceToHost, stream));
+            PREP_CU(cudaStreamSynchronize(stream));
+            certified = hinfo == 0 && hflag[0] == 0 && prod == 0.0;
+        }
+        if (certified) {
+            n_cert++;
+        } else {
+            prep_shift_copy_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, stream>>>(dA, dW, n, addDiag);
+            PREP_CS(cs.Dgetrf(h, n, n, dW, n, dwork, dipiv, dinfo));
+            prep_lu_det_kernel<<<1, 32, 0, stream>>>(dW, dipiv, n, dscal);
+            *launches += 2;
+            n_lu++;
+            double det = 0.0;
+            PREP_CU(cudaMemcpyAsync(&det, dscal, sizeof det, cudaMemcpyDeviceToHost, stream));
+            PREP_CU(cudaStreamSynchronize(stream));
+            if (det > 0) { iters++; break; }
+        }
         iters++;
-        if (det > 0) break;
         addDiag += 0.01;                        // accumulated exactly like util.cpp:219
-        if (iters > 100000) { *why = "the LD matrix never reached a positive determinant"; cleanup(); return -3; }
+        if (iters > 100000) { *why = "the LD matrix never reached a positive determinant"; cleanup2(); cleanup(); return -3; }
     }
     const auto t_psd = tnow();
-    if (trace) fprintf(stderr, "[prep] PSD loop: %d LU factorizations %.1f ms (shift %.2f)\n", iters, tms(t_setup, t_psd), addDiag);
+    if (trace) fprintf(stderr, "[prep] PSD loop: %d shifts (%d LU factorizations, %d Cholesky certificates) %.1f ms (shift %.2f)\n", iters,
+                       n_lu, n_cert, tms(t_setup, t_psd), addDiag);
     // 2. eigen-decomposition of Sigma + a I  (GSL reads the lower triangle of the row-major matrix = the upper
     //    triangle of the column-major view)
     prep_diag_add_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dA, n, addDiag);
     prep_symmetrise_kernel<<<blocks, 256, 0, stream>>>(dA, n);
     *launches += 2;
     PREP_CU(cudaMemcpyAsync(dW, dA, nn * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if (use_chol) {
+        // positive definite after the shift (the usual case): Omega > 0, so B^T B is the matrix itself and
+        // K = S'^T S' = z^T (Sigma + a I)^-1 z -- one Cholesky solve instead of the eigen-decomposition
+        PREP_CS(cs.Dpotrf(h, CUBLAS_FILL_MODE_UPPER, n, dW, n, dwork, lw_ch, dinfo));
+        int hinfo = 0;
+        PREP_CU(cudaMemcpyAsync(&hinfo, dinfo, sizeof hinfo, cudaMemcpyDeviceToHost, stream));
+        PREP_CU(cudaStreamSynchronize(stream));
+        if (hinfo == 0) {
+            PREP_CU(cudaMemcpyAsync(dt, dz, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+            PREP_CS(cs.Dpotrs(h, CUBLAS_FILL_MODE_UPPER, n, 1, dW, n, dt, n, dinfo));
+            prep_dot_kernel<<<1, 256, 0, stream>>>(dz, dt, n, dscal);
+            *launches += 1;
+            double Kc = 0.0;
+            PREP_CU(cudaMemcpyAsync(&Kc, dscal, sizeof Kc, cudaMemcpyDeviceToHost, stream));
+            PREP_CU(cudaStreamSynchronize(stream));
+            if (trace) fprintf(stderr, "[prep] positive definite: K by Cholesky solve %.1f ms\n", tms(t_psd, tnow()));
+            res->add_diag = addDiag; res->K = Kc; res->min_abs_eig = 0.0; res->n_negative = 0; res->psd_iterations = iters;
+            cleanup2();
+            cleanup();
+            return 0;
+        }
+        PREP_CU(cudaMemcpyAsync(dW, dA, nn * sizeof(double), cudaMemcpyDeviceToDevice, stream));   // not definite: the eigen path
+    }
     PREP_CS(cs.Dsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n, dW, n, dev, dwork, std::max(lw_ev, 1), dinfo));
     int info = 0;
     PREP_CU(cudaMemcpyAsync(&info, dinfo, sizeof info, cudaMemcpyDeviceToHost, stream));
@@ -251,6 +381,7 @@ inline int prep_study_device(cudaStream_t stream, int n, double* dA, const doubl
     }
     PREP_CU(cudaGetLastError());
     res->add_diag = addDiag; res->K = sc[0]; res->min_abs_eig = sc[1]; res->n_negative = (int)sc[2]; res->psd_iterations = iters;
+    cleanup2();
     cleanup();
 #undef PREP_CU
 #undef PREP_CS

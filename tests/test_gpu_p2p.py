@@ -21,6 +21,7 @@ def _worker(rank, world, initfile, outdir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from pipsort_b200 import distributed as D
     from oracle import oracle as O
+    from conftest import golden
     dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
     try:
         dev = rank % torch.cuda.device_count()
@@ -44,9 +45,25 @@ def _worker(rank, world, initfile, outdir):
                 assert_results_match(r, want)
             r2 = D.compute_total_likelihood_sharded(e2, 2, collective="p2p")
             if rank == 0:
-                from conftest import golden
                 assert r2.n_configs == 216817
                 assert_results_match(r2, golden("example_c2_p025"))
+            # the repeatable pass (what bench.py times): no reset between passes -- the push empties the senders, the root
+            # sums the peers' slots inside its finalize (few bins) or merges + finalizes (tests/example: ~80 bins)
+            for eng, cc, w in ((e, 3, want), (e2, 2, golden("example_c2_p025"))):
+                eng.reset(); eng.sync()
+                dist.barrier()
+                b = eng.shard_ranks(cc, world)
+                for rep in range(4):
+                    D.pass_exhaustive_sharded(eng, cc, b, collective="p2p")
+                    if rank == 0:
+                        rr = eng.fetch()
+                        assert rr.n_configs == (268 if cc == 3 else 216817)
+                        assert_results_match(rr, w)
+                eng.sync()
+                dist.barrier()
+                leftover = eng.read()                      # every rank's store is empty after a pass
+                assert leftover.n_configs == 0 and leftover.total == 0.0 and not leftover.postValues.any()
+                dist.barrier()
         open(os.path.join(outdir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

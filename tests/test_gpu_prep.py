@@ -118,3 +118,51 @@ def test_slightly_asymmetric_ld_follows_the_reference():
         assert np.array_equal(got_sig, got_sig.T)
         np.testing.assert_allclose(got_sig, want_sig, rtol=0, atol=1e-11)
         assert info["K"] == pytest.approx(want_K, rel=1e-9)
+
+
+def _reference_psd_shift(ld):
+    """makeSigmaPositiveSemiDefinite (util.cpp:195-226) with SciPy's LU: the running product of the pivots in index order."""
+    import scipy.linalg as sl
+    add, it = 0.0, 0
+    n = ld.shape[0]
+    while True:
+        lu, piv = sl.lu_factor(ld + add * np.eye(n))
+        d = -1.0 if (np.count_nonzero(piv != np.arange(n)) % 2) else 1.0
+        for v in np.diag(lu):
+            d *= v
+        it += 1
+        if d > 0:
+            return add, it
+        add += 0.01
+
+
+@pytest.mark.parametrize("n,force", [(600, True), (1100, False)])
+def test_cholesky_certificates_keep_the_reference_shift(n, force):
+    """The PSD loop with most LU factorizations replaced by Cholesky certificates (prep.cuh) must stop at exactly the shift
+    the reference's loop stops at (here: SciPy's partial-pivoting LU + the running pivot product, which underflows for
+    hundreds of SNPs), and K / the effective LD must be those of the eigen path.  n = 600 forces the certificate path on a
+    size the oracle's own pre-processing can check; n = 1100 takes it by default."""
+    import subprocess, sys, json, os
+    from pipsort_b200 import synth
+    L = synth.make_locus(n, overlap=0.8, seed=5)
+    ld, z = L.sigma[0], L.z[0]
+    want_add, want_it = _reference_psd_shift(ld)
+    assert want_it > 2
+    # the threshold is read once per process: run the forced case in a child
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import pipsort_b200 as P; from pipsort_b200 import synth;"
+            "L = synth.make_locus(%d, overlap=0.8, seed=5); s, i = P.preprocess_study(L.sigma[0], L.z[0]);"
+            "print(json.dumps(dict(info=i, dev=float(np.abs(s - (L.sigma[0] + i['add_diag'] * np.eye(%d))).max()), sym=bool((s == s.T).all()))))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), n, n))
+    env = dict(os.environ, PIPSORT_PREP_CHOL_MIN="64" if force else "1024", PIPSORT_TRACE_PREP="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    out = json.loads(p.stdout.strip().splitlines()[-1])
+    assert "Cholesky certificates" in p.stderr and " 0 Cholesky certificates" not in p.stderr, p.stderr
+    assert out["info"]["add_diag"] == want_add and out["info"]["psd_iterations"] == want_it
+    assert out["dev"] <= 1e-12 and out["sym"]
+    K = float(z @ np.linalg.solve(ld + want_add * np.eye(n), z))
+    assert out["info"]["K"] == pytest.approx(K, rel=1e-10)
+    if force:
+        from oracle import oracle as O
+        _, _, o_K, o_add, _, _ = O.preprocess(ld, z)
+        assert o_add == want_add and out["info"]["K"] == pytest.approx(o_K, rel=1e-10)
