@@ -151,10 +151,12 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         if ((err = cudaMemsetAsync(sc->d_counter, 0, 2 * sizeof(unsigned), stream)) != cudaSuccess) return (int)err;
     }
     if (!sc->occ) {
+        // (the attribute is per device: set it for every engine, not once per process)
+        if ((err = cudaFuncSetAttribute(exhaustive_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EXH_SMEM_BYTES)) != cudaSuccess) return (int)err;
         static int occ_cache = 0;    // a property of the kernel and the device generation: query once per process
         static std::mutex occ_mutex;
         std::lock_guard<std::mutex> g(occ_mutex);
-        if (!occ_cache && (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, exhaustive_all_kernel, EXH_WARPS * 32, 0)) != cudaSuccess) return (int)err;
+        if (!occ_cache && (err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, exhaustive_all_kernel, EXH_WARPS * 32, EXH_SMEM_BYTES)) != cudaSuccess) return (int)err;
         sc->occ = occ_cache;
     }
     const double forced = [] { const char* v = getenv("PIPSORT_EXH_CHUNK"); return v ? atof(v) : 0.0; }();   // experiments / tests
@@ -216,7 +218,7 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
     static_assert(sizeof(ExhChunkDesc) == sizeof(int4), "descriptor layout");
     if (sc->plan.n_total == 0) return 0;
     if (ev0 && (err = cudaEventRecord(ev0, stream)) != cudaSuccess) return (int)err;
-    exhaustive_all_kernel<<<sc->plan_blocks, EXH_WARPS * 32, 0, stream>>>(L, sc->plan, Lg);
+    exhaustive_all_kernel<<<sc->plan_blocks, EXH_WARPS * 32, EXH_SMEM_BYTES, stream>>>(L, sc->plan, Lg);
     if (ev1 && (err = cudaEventRecord(ev1, stream)) != cudaSuccess) return (int)err;
     (*launches)++;
     return (int)cudaGetLastError();

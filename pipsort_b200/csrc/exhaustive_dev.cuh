@@ -38,6 +38,7 @@ typedef unsigned long long u64;
 #endif
 constexpr int EXH_WARPS = EXH_WARPS_PER_BLOCK;   // warps per block
 constexpr int EXH_BW = 32;            // max b-window
+constexpr int EXH_PART = 8;           // partial sums kept per b-cell (lanes that survive two shuffle levels)
 constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
 constexpr double FAST_LIMIT = 0x1p+450;
 
@@ -242,7 +243,11 @@ struct WinStudy {
 };
 struct WarpWin {
     WinStudy st[2];
-    double acc[EXH_BW][5];   // b-cell accumulators of the window, flushed at the end of the item
+    // b-cell accumulators of the window, flushed when the window is left.  Eight partial sums per (b, cell): a step's five
+    // b-cell values are folded over the warp only TWO shuffle levels deep (lanes l, l+8, l+16, l+24 -> lane l < 8) and the
+    // eight partial sums go on accumulating in shared memory; the last three levels are paid once per window, not once
+    // per step (the full butterfly was a quarter of the kernel's instructions).
+    double part[EXH_BW][5][EXH_PART];
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
 
@@ -283,7 +288,12 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
         __syncwarp();
         if (lane < nb) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) bin_add(acc, k, b0 + lane, win.acc[lane][k], 0);
+            for (int k = 0; k < 5; k++) {
+                double sm = 0.0;
+#pragma unroll
+                for (int q = 0; q < EXH_PART; q++) sm += win.part[lane][k][(q + lane) & (EXH_PART - 1)];   // (rotated: fewer bank conflicts)
+                bin_add(acc, k, b0 + lane, sm, 0);
+            }
         }
     };
     while (remaining > 0) {
@@ -348,7 +358,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             if (!okb) { win.st[0].v2[lane] = 0.0; win.st[0].v3[lane] = 0.0; win.st[1].v2[lane] = 0.0; win.st[1].v3[lane] = 0.0; }
             win.ok[lane] = okb;
 #pragma unroll
-            for (int k = 0; k < 5; k++) win.acc[lane][k] = 0.0;
+            for (int k = 0; k < 5 * EXH_PART; k++) (&win.part[0][0][0])[k * 32 + lane] = 0.0;
             __syncwarp();
         }
 
@@ -402,15 +412,13 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             double pend[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             int pend_t = -1;
             auto reduce_pending = [&]() {
-                double mine = 0.0;
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
                     double r = pend[k];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                    if (lane == k) mine = r;
+                    r += __shfl_xor_sync(0xffffffffu, r, 16);
+                    r += __shfl_xor_sync(0xffffffffu, r, 8);
+                    if (lane < EXH_PART) win.part[pend_t][k][lane] += r;
                 }
-                if (lane < 5) win.acc[pend_t][lane] += mine;
             };
             // steps of this segment: the b's of the window that have an x of this tile beyond them, from t_lo on, as
             // far as the chunk reaches
@@ -616,9 +624,9 @@ struct ExhAll {
 
 __global__ void __launch_bounds__(EXH_WARPS * 32, EXH_MINBLOCKS)
 exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
-    __shared__ WarpWin wins[EXH_WARPS];
+    extern __shared__ __align__(16) unsigned char exh_smem[];      // EXH_WARPS x WarpWin (more than the 48 KB static limit)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpWin& win = wins[wib];
+    WarpWin& win = reinterpret_cast<WarpWin*>(exh_smem)[wib];
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(A.counter, 1u);
@@ -651,5 +659,7 @@ exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
         if (done == gridDim.x - 1) { A.counter[0] = 0u; A.counter[1] = 0u; }
     }
 }
+
+constexpr size_t EXH_SMEM_BYTES = sizeof(WarpWin) * EXH_WARPS;
 
 }  // namespace pipsort
