@@ -323,18 +323,18 @@ struct pipsort_engine {
         double* d_out_l = nullptr; int* d_batch = nullptr; unsigned char* d_upd = nullptr; int* d_unseen = nullptr;
         int* d_counter = nullptr; double* d_scored = nullptr;
         unsigned char* d_state = nullptr; int* d_pos_of = nullptr; double* d_total = nullptr;   // sharded search only
-        u64 epoch = 0;              // rounds of the sharded search since the engine was created (flags of the exchange)
         double* h_out_l = nullptr;  // pinned: [n_max] neighbour values + 1 slot reused for the counter
         long long n_max = 0; int kmax = 0;
     } sss;
     // peer-memory combine (p2p.cuh): this rank's mailbox + the peers' mapped mailboxes
     struct P2P {
-        double* mailbox = nullptr;   // world slots (16 bytes per accumulator double) | 8 control words
+        double* mailbox = nullptr;   // 256-byte header (8 control words) | world slots (16 bytes per accumulator double)
         unsigned* d_done = nullptr;
         void* peer_base[P2P_MAX_WORLD] = {nullptr};
         P2PPeers peers;
         int world = 0, rank = 0, root = 0;
-        u64 epoch = 0;
+        int cache_slot = -1;         // entry of the process-wide mailbox cache this engine has borrowed
+        u64* sss_epoch = nullptr;    // rounds of the sharded search on this mailbox (lives with the mailbox, not the engine)
         bool connected = false;
     } p2p;
     PrepResult prep[2];             // PIPSORT_RAW_LD: what the on-device pre-processing found per study
@@ -462,6 +462,52 @@ struct WorkModel {
     double configs_first(int j, int g) const { return j == 0 ? 1.0 : w[g] * E[j - 1][g + 1]; }
 };
 
+// ---- mailboxes of the peer-memory combine step (p2p.cuh), cached per process ----------------------------------------------
+// A fine-mapping run creates one engine per locus; cudaMalloc + IPC export + the peers' cudaIpcOpenMemHandle cost far more
+// than evaluating a 150-SNP locus.  Mailboxes therefore belong to the process: an engine borrows one that is large enough
+// (or allocates it) and hands it back at destroy; peers' mappings are opened once per distinct handle and kept.  The
+// control words sit in a fixed header at the START of the mailbox, so epochs and flow control carry over from one engine
+// to the next whatever their slot size (slot contents are self-validating by epoch: stale data never matches).
+constexpr size_t P2P_HDR_BYTES = 256;
+struct MailboxEntry {
+    int device, world;
+    double* mailbox; size_t bytes; unsigned* d_done;
+    u64 sss_epoch;
+    bool in_use;
+};
+std::vector<MailboxEntry*>& mailbox_cache() { static std::vector<MailboxEntry*> c; return c; }
+std::mutex& mailbox_mutex() { static std::mutex m; return m; }
+
+int mailbox_acquire(int device, int world, size_t bytes, int* slot) {
+    std::lock_guard<std::mutex> g(mailbox_mutex());
+    auto& c = mailbox_cache();
+    for (size_t i = 0; i < c.size(); i++)
+        if (!c[i]->in_use && c[i]->device == device && c[i]->world == world && c[i]->bytes >= bytes) { c[i]->in_use = true; *slot = (int)i; return 0; }
+    MailboxEntry* m = new MailboxEntry{device, world, nullptr, bytes + bytes / 2, nullptr, 0, true};
+    CU(cudaMalloc(&m->mailbox, m->bytes));                   // cudaMalloc (not the pool): CUDA IPC needs it
+    CU(cudaMemset(m->mailbox, 0, m->bytes));
+    CU(cudaMalloc(&m->d_done, sizeof(unsigned)));
+    CU(cudaMemset(m->d_done, 0, sizeof(unsigned)));
+    c.push_back(m);
+    *slot = (int)c.size() - 1;
+    return 0;
+}
+void mailbox_release(int slot) {
+    std::lock_guard<std::mutex> g(mailbox_mutex());
+    mailbox_cache()[slot]->in_use = false;
+}
+// a peer's mailbox, mapped once per distinct IPC handle
+int peer_map(int device, const cudaIpcMemHandle_t& h, void** base) {
+    static std::vector<std::pair<std::string, void*>> maps;
+    std::lock_guard<std::mutex> g(mailbox_mutex());
+    const std::string key = std::to_string(device) + ":" + std::string(reinterpret_cast<const char*>(&h), sizeof h);
+    for (auto& kv : maps) if (kv.first == key) { *base = kv.second; return 0; }
+    CU(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));
+    maps.emplace_back(key, *base);
+    return 0;
+}
+inline ulonglong2* p2p_slots(void* base) { return reinterpret_cast<ulonglong2*>(static_cast<char*>(base) + P2P_HDR_BYTES); }
+
 }  // namespace
 
 extern "C" {
@@ -489,9 +535,7 @@ void pipsort_destroy(pipsort_engine* e) {
     }
     {
         pipsort_engine::P2P& q = e->p2p;
-        for (int r = 0; r < P2P_MAX_WORLD; r++) if (q.peer_base[r] && r != q.rank) cudaIpcCloseMemHandle(q.peer_base[r]);
-        if (q.mailbox) cudaFree(q.mailbox);
-        if (q.d_done) cudaFree(q.d_done);
+        if (q.cache_slot >= 0) mailbox_release(q.cache_slot);   // mailbox, counters and peer mappings stay with the process
     }
     for (cudaGraphExec_t x : e->graphs) cudaGraphExecDestroy(x);
     if (e->d_idx) cudaFree(e->d_idx);
@@ -1288,7 +1332,7 @@ int pipsort_sss_sharded(pipsort_engine* e, int max_causal, int max_iterations, i
         const long long n = nz + nm + np;
         if ((rc = sss_table_reserve(e, q.count + (u64)n))) return rc;
         // this round's exchange: epoch flag + the half of the slots it uses
-        const u64 epoch = ++q.epoch;
+        const u64 epoch = ++*pp.sss_epoch;
         SssShard sh;
         memset(&sh, 0, sizeof sh);
         sh.world = world; sh.rank = rank;
@@ -1296,8 +1340,8 @@ int pipsort_sss_sharded(pipsort_engine* e, int max_causal, int max_iterations, i
         const size_t hoff = acc_len + (size_t)(epoch & 1) * half;
         for (int p = 0; p < world; p++) {
             if (p == rank) continue;
-            sh.peer_slot[p] = static_cast<ulonglong2*>(pp.peer_base[p]) + (size_t)rank * stride + hoff;
-            sh.my_slot[p] = reinterpret_cast<const ulonglong2*>(pp.mailbox) + (size_t)p * stride + hoff;
+            sh.peer_slot[p] = p2p_slots(pp.peer_base[p]) + (size_t)rank * stride + hoff;
+            sh.my_slot[p] = p2p_slots(pp.mailbox) + (size_t)p * stride + hoff;
         }
         CU(cudaMemsetAsync(q.d_counter, 0, 2 * sizeof(int), e->stream));
         const unsigned gb = (unsigned)((n + 1 + 255) / 256);
@@ -1655,11 +1699,13 @@ int pipsort_p2p_export(pipsort_engine* e, int world, void* handle) {
     pipsort_engine::P2P& q = e->p2p;
     if (q.mailbox && q.world != world) return fail(PIPSORT_E_ARG, "mailbox already exported for world=%d", q.world);
     if (!q.mailbox) {
-        const size_t bytes = (size_t)world * p2p_slot_len(e) * sizeof(ulonglong2) + 8 * sizeof(u64);
-        CU(cudaMalloc(&q.mailbox, bytes));                       // cudaMalloc (not the pool): CUDA IPC needs it
-        CU(cudaMemset(q.mailbox, 0, bytes));
-        CU(cudaMalloc(&q.d_done, sizeof(unsigned)));
-        CU(cudaMemset(q.d_done, 0, sizeof(unsigned)));
+        const size_t bytes = P2P_HDR_BYTES + (size_t)world * p2p_slot_len(e) * sizeof(ulonglong2);
+        int rc = mailbox_acquire(e->device, world, bytes, &q.cache_slot);
+        if (rc) return rc;
+        MailboxEntry* m = mailbox_cache()[q.cache_slot];
+        q.mailbox = m->mailbox;
+        q.d_done = m->d_done;
+        q.sss_epoch = &m->sss_epoch;
         q.world = world;
     }
     cudaIpcMemHandle_t h;
@@ -1679,18 +1725,17 @@ int pipsort_p2p_connect(pipsort_engine* e, const void* handles, int world, int r
     CU(cudaSetDevice(e->device));
     q.rank = rank; q.root = root;
     q.peers.world = world; q.peers.root = root;
-    const size_t ctrl_off = (size_t)world * p2p_slot_len(e) * 2;   // in 8-byte words
     for (int r = 0; r < world; r++) {
         void* base = q.mailbox;
         if (r != rank) {
             cudaIpcMemHandle_t h;
             memcpy(&h, (const char*)handles + (size_t)r * PIPSORT_IPC_HANDLE_BYTES, sizeof h);
-            CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            int rc = peer_map(e->device, h, &base);
+            if (rc) return rc;
         }
         q.peer_base[r] = base;
-        q.peers.ctrl[r] = reinterpret_cast<u64*>(static_cast<double*>(base) + ctrl_off);
+        q.peers.ctrl[r] = reinterpret_cast<u64*>(base);          // the control words open the mailbox
     }
-    q.epoch = 0;
     q.connected = true;
     return 0;
 }
@@ -1730,7 +1775,7 @@ int pipsort_p2p_combine_finalize(pipsort_engine* e) {
     cfg.attrs = at;
     cfg.numAttrs = no_pdl ? 0 : 1;
     double* errf = e->L.acc.counters + 1 + ERR_P2P_TIMEOUT;
-    CU(cudaLaunchKernelEx(&cfg, finalize_merge_kernel, e->L.acc, U, cx, cy, e->d_res, reinterpret_cast<const ulonglong2*>(q.mailbox),
+    CU(cudaLaunchKernelEx(&cfg, finalize_merge_kernel, e->L.acc, U, cx, cy, e->d_res, p2p_slots(q.mailbox),
                           p2p_slot_len(e), e->bins_len, q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf));
     e->launches++;
     return 0;
@@ -1756,10 +1801,10 @@ static int p2p_reduce_impl(pipsort_engine* e, bool clear_sender) {
     cfg.attrs = at;
     cfg.numAttrs = no_pdl ? 0 : 1;
     if (q.rank != q.root) {
-        CU(cudaLaunchKernelEx(&cfg, p2p_push_kernel, e->L.acc.bins, n, static_cast<ulonglong2*>(q.peer_base[q.root]) + (size_t)q.rank * slot,
+        CU(cudaLaunchKernelEx(&cfg, p2p_push_kernel, e->L.acc.bins, n, p2p_slots(q.peer_base[q.root]) + (size_t)q.rank * slot,
                               q.peers.ctrl[q.rank], q.d_done, errf, clear_sender ? 1 : 0));
     } else {
-        CU(cudaLaunchKernelEx(&cfg, p2p_merge_kernel, e->L.acc.bins, reinterpret_cast<const ulonglong2*>(q.mailbox), n, slot,
+        CU(cudaLaunchKernelEx(&cfg, p2p_merge_kernel, e->L.acc.bins, (const ulonglong2*)p2p_slots(q.mailbox), n, slot,
                               q.peers.ctrl[q.rank], q.peers, q.rank, q.d_done, errf));
     }
     e->launches++;

@@ -61,29 +61,41 @@ def slice_bounds(n, world):
     return [(n * r) // world for r in range(world + 1)]
 
 
+_handle_cache = {}
+
+
 def connect_p2p(engine, group=None, root=0):
     """Exchange the engines' mailbox handles (CUDA IPC) over the group and map every peer: after this the combine step
     can run over NVLink peer memory (collective="p2p") instead of NCCL.  Returns False when IPC mapping is not possible
-    (the caller then stays with the all-reduce)."""
+    (the caller then stays with the all-reduce).
+
+    Mailboxes belong to the process, not to the engine (the library hands the same one to the next engine that fits), so
+    the table of handles is exchanged once and reused while this rank's handle stays the same -- a run that creates one
+    engine per locus pays the all_gather_object once, not per locus.  (All ranks run the same sequence of loci, so they
+    all hit or all miss.)"""
     world, rank = world_and_rank(group)
     if world == 1:
         return False
-    ok, mine = True, b""
     try:
         mine = engine.p2p_export(world)
     except Exception:
-        ok = False
-    handles = [None] * world
-    _dist().all_gather_object(handles, mine if ok else b"", group=group)
-    if any(len(h) == 0 for h in handles):
-        return False
+        mine = b""
+    key = (id(group), world, rank, root)
+    cached = _handle_cache.get(key)
+    if mine and cached is not None and cached[rank] == mine:
+        handles = cached
+    else:
+        handles = [None] * world
+        _dist().all_gather_object(handles, mine, group=group)
+        if any(len(h) == 0 for h in handles):
+            return False
+        _handle_cache[key] = handles
     try:
         engine.p2p_connect(handles, rank, root)
     except Exception:
-        ok = False
-    flags = [None] * world
-    _dist().all_gather_object(flags, ok, group=group)
-    return all(flags)
+        _handle_cache.pop(key, None)
+        return False
+    return True
 
 
 def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allreduce"):
