@@ -82,20 +82,24 @@ def connect_p2p(engine, group=None, root=0):
         mine = b""
     key = (id(group), world, rank, root)
     cached = _handle_cache.get(key)
+    if cached == "unavailable":
+        return False                       # every rank recorded the same verdict (it was agreed below)
     if mine and cached is not None and cached[rank] == mine:
-        handles = cached
-    else:
-        handles = [None] * world
-        _dist().all_gather_object(handles, mine, group=group)
-        if any(len(h) == 0 for h in handles):
-            return False
-        _handle_cache[key] = handles
-    try:
-        engine.p2p_connect(handles, rank, root)
-    except Exception:
-        _handle_cache.pop(key, None)
-        return False
-    return True
+        engine.p2p_connect(cached, rank, root)
+        return True
+    handles = [None] * world
+    _dist().all_gather_object(handles, mine, group=group)
+    ok = all(len(h) > 0 for h in handles)
+    if ok:
+        try:
+            engine.p2p_connect(handles, rank, root)
+        except Exception:
+            ok = False
+    flags = [None] * world
+    _dist().all_gather_object(flags, ok, group=group)
+    ok = all(flags)
+    _handle_cache[key] = handles if ok else "unavailable"
+    return ok
 
 
 def run_exhaustive_sharded(engine, c, group=None, bounds=None, collective="allreduce"):
