@@ -508,24 +508,27 @@ def main():
         d_out = torch.zeros(width, dtype=torch.float64, device=dev)
         d_all = torch.empty(world * width, dtype=torch.float64, device=dev) if world > 1 else None
 
-        def one():
+        def one(gather):
             e.score_union_configs_device(d_idx.data_ptr(), hi - lo, cc, 0, d_out.data_ptr())
-            if world > 1:
+            if gather:
                 dist.all_gather_into_tensor(d_all, d_out)
 
-        for _ in range(3):
-            one()
-        e.sync(); e.reset(); barrier()
-        reps = 10
-        evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, z in evp:
-            a.record(stream); one(); z.record(stream)
-        barrier()
-        ms = float(np.mean([a.elapsed_time(z) for a, z in evp]))
-        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        ms = float(t_ms.item())
+        def timed(gather):
+            for _ in range(3):
+                one(gather)
+            e.sync(); e.reset(); barrier()
+            reps = 10
+            evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, z in evp:
+                a.record(stream); one(gather); z.record(stream)
+            barrier()
+            t_ms = torch.tensor([float(np.mean([a.elapsed_time(z) for a, z in evp]))], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+            return float(t_ms.item())
+
+        ms = timed(False)                       # scoring launch of this rank's slice, max over ranks
+        ms_nccl = timed(True) if world > 1 else None
         sh = (Ld.snp_map[0] >= 0) & (Ld.snp_map[1] >= 0)
         n_exp, flops, gather = 0, 0.0, 0
         for v in rows:
@@ -535,19 +538,29 @@ def main():
             flops += f; n_exp += n
             k0, k1 = int((Ld.snp_map[0][v] >= 0).sum()) if len(v) else 0, int((Ld.snp_map[1][v] >= 0).sum()) if len(v) else 0
             gather += 8 * (k0 * k0 + k1 * k1)
-        # the whole search (device-resident search state), rank 0 only
+        # the whole search (device-resident search state; with N GPUs: pipsort_sss_sharded -- every round's neighbourhood
+        # split over the ranks, the values exchanged through the peer-memory mailboxes): host wall clock, max over ranks
         sss = None
-        if rank == 0:
-            e.reset()
-            t1 = time.perf_counter(); rs, it, why = e.sss(cc); dt = time.perf_counter() - t1
-            t1 = time.perf_counter(); rs, it, why = e.sss(cc); dt = time.perf_counter() - t1
-            sss = {"rounds": it, "stop_reason": why, "configs": rs.n_configs, "ms_total": 1e3 * dt, "ms_per_round": 1e3 * dt / max(it, 1)}
+        e.set_stream(0)
+        if world == 1 or D.connect_p2p(e):
+            for rep in range(2):
+                barrier()
+                t1 = time.perf_counter()
+                rs, it, why = D.sss_sharded(e, cc)
+                dt = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                dtv = float(dt.item())
+                sss = {"rounds": it, "stop_reason": why, "configs": rs.n_configs, "ms_total": 1e3 * dtv, "ms_per_round": 1e3 * dtv / max(it, 1),
+                       "what": "pipsort_sss" if world == 1 else "pipsort_sss_sharded + combine over peer memory + read on the root"}
         if world > 1:
             dist.barrier()
         e.close()
         return {"workload": f"D5000c5_sss: synthetic 5000+5000 SNPs, U={U}, c=5; ONE neighbourhood of a 4-SNP state = {len(rows)} union "
                             f"configurations, {n_exp} expanded configurations, sliced over {world} GPU(s)",
                 "ms_per_neighbourhood": ms, "value": n_exp / (ms * 1e-3), "unit": UNIT,
+                "ms_with_nccl_allgather_of_the_values": ms_nccl,
                 "union_configs_per_s": len(rows) / (ms * 1e-3),
                 "roofline": {"bound": "fp64", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                              "frac": flops / (ms * 1e-3) / peak, "flop_per_launch": flops,

@@ -18,6 +18,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _worker(rank, world, initfile, outdir):
+    import faulthandler
+    faulthandler.dump_traceback_later(120, exit=True)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from pipsort_b200 import distributed as D
     from oracle import oracle as O
@@ -76,6 +78,8 @@ def test_two_ranks_combine_over_peer_memory():
 
 
 def _nccl_worker(rank, world, initfile, outdir):
+    import faulthandler
+    faulthandler.dump_traceback_later(120, exit=True)          # a hung collective must not hang the suite
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from pipsort_b200 import distributed as D
     from oracle import oracle as O
@@ -121,6 +125,8 @@ def test_two_ranks_nccl_allreduce_without_stream_binding():
 
 
 def _sss_worker(rank, world, initfile, outdir):
+    import faulthandler
+    faulthandler.dump_traceback_later(120, exit=True)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from pipsort_b200 import distributed as D
     from pipsort_b200 import synth
