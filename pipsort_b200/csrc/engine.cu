@@ -219,6 +219,35 @@ finalize_merge_kernel(AccDev acc, int U, double cx, double cy, double* __restric
     auto take = [&](size_t idx) -> double {                        // element idx of the store, summed over all GPUs; own copy cleared
         double v = acc.bins[idx];
         if (v != 0.0) acc.bins[idx] = 0.0;
+        if (peers.world <= 8) {
+            // all peers' copies are requested at once (one round trip, not one per peer: with 7 peers the serial polls were
+            // most of the step at N = 8), re-requested until each carries this epoch's flag, then added in rank order
+            u64 w0[8], w1[8];
+            unsigned pend = 0;
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                if (r < peers.world && r != my_rank) {
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[r]), "=l"(w1[r]) : "l"(slots + (size_t)r * slot_stride + idx));
+                    pend |= 1u << r;
+                }
+            const long long t0 = clock64();
+            for (;;) {
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if ((pend >> r & 1) && (w0[r] >> 32) == flag && (w1[r] >> 32) == flag) pend &= ~(1u << r);
+                if (!pend) break;
+                if (clock64() - t0 > P2P_SPIN_CYCLES) { ok = false; break; }
+                __nanosleep(32);
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (pend >> r & 1)
+                        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[r]), "=l"(w1[r]) : "l"(slots + (size_t)r * slot_stride + idx));
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                if (r < peers.world && r != my_rank) v += __longlong_as_double((long long)((w0[r] & 0xffffffffull) | (w1[r] << 32)));
+            return v;
+        }
         for (int r = 0; r < peers.world; r++)
             if (r != my_rank) v += p2p_take(slots + (size_t)r * slot_stride + idx, flag, ok);
         return v;
