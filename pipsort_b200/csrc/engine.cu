@@ -4,6 +4,7 @@
 // score.cuh (generic, warp per union configuration) and exhaustive.cuh (register kernel, lane per
 // union subset).  No CPU compute path exists: without a usable CUDA device every entry point fails.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -13,6 +14,7 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pipsort_b200.h"
@@ -1604,48 +1606,71 @@ int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_
     return rc;
 }
 
-int pipsort_posterior_exhaustive_batch(const pipsort_locus* loci, int32_t n_loci, int device, uint32_t flags, int c,
-                                       const pipsort_outputs* outs, uint64_t* n_configs) {
-    if (n_loci < 0 || (n_loci > 0 && (!loci || !outs))) return fail(PIPSORT_E_ARG, "bad argument");
-    // Software pipeline over DEPTH engines, each on its own stream: while locus i is being evaluated the uploads and the
-    // preparation launches of locus i+1 are already queued, and the results of locus i-DEPTH+1 are being copied back.
-    // Every locus still pays its own host -> device copy, kernels and device -> host read; only the waiting overlaps.
+// loci first, first + stride, first + 2 stride, ... through a software pipeline over DEPTH engines, each on its own stream:
+// while locus i is being evaluated the uploads and the preparation launches of the next one are already queued, and the
+// results of the one DEPTH before are being copied back.  Every locus still pays its own host -> device copy, kernels and
+// device -> host read; only the waiting overlaps.  `stop` is raised by the first worker that fails.
+static int batch_worker(const pipsort_locus* loci, int32_t n_loci, int first, int stride, int device, uint32_t flags, int c,
+                        const pipsort_outputs* outs, uint64_t* n_configs, std::atomic<int>* stop, std::string* err) {
     constexpr int DEPTH = 3;
     pipsort_engine* inflight[DEPTH] = {nullptr, nullptr, nullptr};
+    int idx_of[DEPTH] = {-1, -1, -1};
     int rc = 0;
-    auto finish = [&](int i) -> int {          // results of locus i (slot i % DEPTH)
-        pipsort_engine*& e = inflight[i % DEPTH];
-        int r = read_complete(e, &outs[i]);
-        if (!r && n_configs) n_configs[i] = e->last_read_count;
+    auto finish = [&](int slot) -> int {       // results of the locus in pipeline slot `slot`
+        pipsort_engine*& e = inflight[slot];
+        int r = read_complete(e, &outs[idx_of[slot]]);
+        if (!r && n_configs) n_configs[idx_of[slot]] = e->last_read_count;
         std::string keep = g_err;
         pipsort_destroy(e);
         g_err = keep;
         e = nullptr;
         return r;
     };
-    int i = 0;
-    for (; i < n_loci && !rc; i++) {
-        if (i >= DEPTH) rc = finish(i - DEPTH);
+    int k = 0;
+    for (int i = first; i < n_loci && !rc && !stop->load(std::memory_order_relaxed); i += stride, k++) {
+        const int slot = k % DEPTH;
+        if (inflight[slot]) rc = finish(slot);
         if (rc) break;
         pipsort_engine* e = nullptr;
         rc = pipsort_create(&loci[i], device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT, &e);
         if (rc) break;
-        inflight[i % DEPTH] = e;
+        inflight[slot] = e;
+        idx_of[slot] = i;
         uint64_t total = 0;
         rc = pipsort_total_ranks(e, c, &total);
         if (!rc) rc = pipsort_run_exhaustive(e, c, 0, total);
         if (!rc) rc = read_enqueue(e);
     }
-    // drain (also after an error: every engine still in flight is destroyed)
-    const int issued = i;
-    for (int j = std::max(0, issued - DEPTH); j < issued; j++) {
-        if (!inflight[j % DEPTH]) continue;
-        if (!rc) rc = finish(j);
-        else { std::string keep = g_err; pipsort_destroy(inflight[j % DEPTH]); g_err = keep; inflight[j % DEPTH] = nullptr; }
+    // drain in issue order (also after an error: every engine still in flight is destroyed)
+    for (int d = 0; d < DEPTH; d++) {
+        const int slot = (k + d) % DEPTH;
+        if (!inflight[slot]) continue;
+        if (!rc && !stop->load(std::memory_order_relaxed)) rc = finish(slot);
+        else { std::string keep = g_err; pipsort_destroy(inflight[slot]); g_err = keep; inflight[slot] = nullptr; }
     }
-    for (int d = 0; d < DEPTH; d++)
-        if (inflight[d]) { std::string keep = g_err; pipsort_destroy(inflight[d]); g_err = keep; }
+    if (rc) { stop->store(1); *err = g_err; }
     return rc;
+}
+
+int pipsort_posterior_exhaustive_batch(const pipsort_locus* loci, int32_t n_loci, int device, uint32_t flags, int c,
+                                       const pipsort_outputs* outs, uint64_t* n_configs) {
+    if (n_loci < 0 || (n_loci > 0 && (!loci || !outs))) return fail(PIPSORT_E_ARG, "bad argument");
+    // The host side of a small locus (a dozen runtime calls, ~60 us) costs as much as its evaluation on the device: long lists
+    // are issued by TWO host threads (PIPSORT_BATCH_THREADS), each with its own pipeline over its own engines and streams,
+    // loci dealt alternately; the device serialises the exhaustive kernels anyway (each fills the GPU).
+    static const int want = [] { const char* v = getenv("PIPSORT_BATCH_THREADS"); return v ? std::max(1, std::min(8, atoi(v))) : 2; }();
+    const int T = n_loci >= 8 ? want : 1;
+    std::atomic<int> stop(0);
+    std::vector<std::string> errs(T);
+    std::vector<int> rcs(T, 0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++)
+        th.emplace_back([&, t] { rcs[t] = batch_worker(loci, n_loci, t, T, device, flags, c, outs, n_configs, &stop, &errs[t]); });
+    rcs[0] = batch_worker(loci, n_loci, 0, T, device, flags, c, outs, n_configs, &stop, &errs[0]);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; t++)
+        if (rcs[t]) { g_err = errs[t]; return rcs[t]; }
+    return 0;
 }
 
 int pipsort_last_read_config_count(const pipsort_engine* e, uint64_t* out) {

@@ -432,46 +432,89 @@ def posterior_exhaustive(num_snps, sigma, z, d, K, snp_map, c, gamma=0.01, shari
     return Results(float(total[0]), post, nc, sp, sl, nl, int(cnt.value))
 
 
+_LOCUS_DT = np.dtype([("num_studies", "<i4"), ("num_snps", "<u8"), ("sigma", "<u8"), ("z", "<u8"), ("d", "<u8"), ("K", "<f8"),
+                      ("union_count", "<i4"), ("snp_map", "<u8"), ("gamma", "<f8"), ("sharing_param", "<f8"),
+                      ("max_causal", "<i4")], align=True)            # == struct pipsort_locus (checked against ctypes below)
+_OUT_DT = np.dtype([(n, "<u8") for n in ("total", "postValues", "noCausal", "sharedPips", "sharedLL", "notSharedLL")])
+assert _LOCUS_DT.itemsize == C.sizeof(_LocusV) and _OUT_DT.itemsize == C.sizeof(_OutputsV)
+assert all(_LOCUS_DT.fields[n][1] == getattr(_LocusV, n).offset for n, _ in _LocusV._fields_)
+
+
+def _ready(a, dtype):
+    """a as a C-contiguous array of dtype (no copy when it already is one)."""
+    if type(a) is np.ndarray and a.dtype == dtype and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class LocusBatch:
+    """The argument block of pipsort_posterior_exhaustive_batch, built once: arrays of `pipsort_locus` / `pipsort_outputs`
+    structs (numpy structured arrays filled column by column) that point into the caller's host arrays, and ONE result
+    buffer for all loci.  run() is the C-ABI call and nothing else; results() slices the buffer into Results.
+    loci: sequence of dicts with the keys of posterior_exhaustive's arguments (num_snps, sigma, z, d, K, snp_map and
+    optionally gamma, sharing_param); sigma / z flat float64 arrays (studies concatenated)."""
+
+    def __init__(self, loci, c, device=0, raw_ld=False):
+        n = self.n = len(loci)
+        self.c, self.device, self.flags = int(c), int(device), RAW_LD if raw_ld else 0
+        f64, i32 = np.dtype(np.float64), np.dtype(np.int32)
+        ns = [_ready(Lc["num_snps"], i32) for Lc in loci]
+        sg = [_ready(Lc["sigma"], f64) for Lc in loci]
+        zz = [_ready(Lc["z"], f64) for Lc in loci]
+        dd = [_ready(Lc["d"], f64) for Lc in loci]
+        sm = [_ready(Lc["snp_map"], i32) for Lc in loci]
+        self._keep = (ns, sg, zz, dd, sm)                    # the structs hold raw pointers into these
+        ptr = lambda arrs: [a.ctypes.data for a in arrs]     # noqa: E731
+        S = self.S = np.fromiter((a.shape[0] for a in ns), dtype=np.int64, count=n)
+        U = self.U = np.fromiter((a.shape[1] for a in sm), dtype=np.int64, count=n)
+        N = self.N = np.fromiter((sum(a.tolist()) for a in ns), dtype=np.int64, count=n)
+        la = self.la = np.zeros(n, dtype=_LOCUS_DT)
+        la["num_studies"] = S
+        la["num_snps"] = ptr(ns); la["sigma"] = ptr(sg); la["z"] = ptr(zz); la["d"] = ptr(dd); la["snp_map"] = ptr(sm)
+        la["K"] = [Lc["K"] for Lc in loci]
+        la["union_count"] = U
+        la["gamma"] = [Lc.get("gamma", 0.01) for Lc in loci]
+        la["sharing_param"] = [Lc.get("sharing_param", 0.75) for Lc in loci]
+        la["max_causal"] = self.c
+        # one result buffer: per locus total | postValues[N] | noCausal[S] | sharedPips[U] | sharedLL[U] | notSharedLL[U]
+        off = self.off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(1 + N + S + 3 * U, out=off[1:])
+        buf = self.buf = np.empty(int(off[-1]))
+        b0 = buf.ctypes.data + 8 * off[:-1]
+        oa = self.oa = np.zeros(n, dtype=_OUT_DT)
+        oa["total"] = b0
+        oa["postValues"] = b0 + 8
+        oa["noCausal"] = b0 + 8 * (1 + N)
+        oa["sharedPips"] = b0 + 8 * (1 + N + S)
+        oa["sharedLL"] = b0 + 8 * (1 + N + S + U)
+        oa["notSharedLL"] = b0 + 8 * (1 + N + S + 2 * U)
+        self.cnt = np.zeros(n, dtype=np.uint64)
+        self._args = (C.cast(la.ctypes.data, C.POINTER(_LocusV)), n, self.device, self.flags, self.c,
+                      C.cast(oa.ctypes.data, C.POINTER(_OutputsV)), C.cast(self.cnt.ctypes.data, C.POINTER(C.c_uint64)))
+
+    def run(self):
+        """pipsort_posterior_exhaustive_batch: host buffers in, host buffers out."""
+        if self.n:
+            _check(lib().pipsort_posterior_exhaustive_batch(*self._args))
+        return self
+
+    def results(self):
+        out, buf = [], self.buf
+        offl, Nl, Sl, Ul, cl = self.off.tolist(), self.N.tolist(), self.S.tolist(), self.U.tolist(), self.cnt.tolist()
+        for i in range(self.n):
+            o, Ni, Si, Ui = offl[i], Nl[i], Sl[i], Ul[i]
+            p1 = o + 1 + Ni
+            p2 = p1 + Si
+            out.append(Results(float(buf[o]), buf[o + 1:p1], buf[p1:p2], buf[p2:p2 + Ui], buf[p2 + Ui:p2 + 2 * Ui],
+                               buf[p2 + 2 * Ui:p2 + 3 * Ui], cl[i]))
+        return out
+
+
 def posterior_exhaustive_batch(loci, c, device=0, raw_ld=False):
     """A list of loci in one call (pipsort_posterior_exhaustive_batch): the engine pipelines them over three streams, so
     the uploads / preparation of the next locus and the read-back of the previous one overlap the current evaluation.
-    loci: sequence of dicts with the keys of posterior_exhaustive's arguments (num_snps, sigma, z, d, K, snp_map and
-    optionally gamma, sharing_param); sigma / z flat float64 arrays (studies concatenated).  Returns a list of Results."""
-    n = len(loci)
-    arr_l = (_LocusV * n)()
-    arr_o = (_OutputsV * n)()
-    keep, views, seen = [], [], {}
-
-    def prepared(a, dtype):        # (contiguous array, address), memoised per input object: loci often share arrays
-        hit = seen.get(id(a))
-        if hit is None:
-            b = np.ascontiguousarray(a, dtype=dtype)
-            hit = seen[id(a)] = (b, b.ctypes.data)
-            keep.append((a, b))
-        return hit
-
-    for i, Lc in enumerate(loci):
-        num_snps, p_ns = prepared(Lc["num_snps"], np.int32)
-        sigma, p_sig = prepared(Lc["sigma"], np.float64)
-        z, p_z = prepared(Lc["z"], np.float64)
-        d, p_d = prepared(Lc["d"], np.float64)
-        smap, p_map = prepared(Lc["snp_map"], np.int32)
-        S, U, N = len(num_snps), int(smap.shape[1]), int(num_snps.sum())
-        buf = np.zeros(1 + N + S + 3 * U)
-        keep.append(buf)
-        arr_l[i] = _LocusV(S, p_ns, p_sig, p_z, p_d, float(Lc["K"]), U, p_map, float(Lc.get("gamma", 0.01)),
-                           float(Lc.get("sharing_param", 0.75)), int(c))
-        b0 = buf.ctypes.data
-        arr_o[i] = _OutputsV(b0, b0 + 8, b0 + 8 * (1 + N), b0 + 8 * (1 + N + S), b0 + 8 * (1 + N + S + U),
-                             b0 + 8 * (1 + N + S + 2 * U))
-        views.append((buf, N, S, U))
-    cnt = (C.c_uint64 * n)()
-    _check(lib().pipsort_posterior_exhaustive_batch(arr_l, n, int(device), RAW_LD if raw_ld else 0, int(c), arr_o, cnt))
-    out = []
-    for i, (buf, N, S, U) in enumerate(views):
-        out.append(Results(float(buf[0]), buf[1:1 + N], buf[1 + N:1 + N + S], buf[1 + N + S:1 + N + S + U],
-                           buf[1 + N + S + U:1 + N + S + 2 * U], buf[1 + N + S + 2 * U:], int(cnt[i])))
-    return out
+    Returns a list of Results.  (LocusBatch separates building the argument block from the call itself.)"""
+    return LocusBatch(loci, c, device, raw_ld).run().results()
 
 
 def preprocess_study(ld, z, device=0):
