@@ -199,9 +199,10 @@ int pipsort_config_count(pipsort_engine* e, uint64_t* out);
 int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_t flags, int c, const pipsort_outputs* out,
                                  uint64_t* n_configs);
 
-/* The same for a list of loci (a fine-mapping run has thousands): a software pipeline over three engines on three
- * streams, so that the uploads and preparation launches of the next locus and the read-back of the previous one overlap
- * the evaluation of the current one.  loci[i] -> outs[i] (and n_configs[i], optional).  Stops at the first error.   */
+/* The same for a list of loci (a fine-mapping run has thousands): software pipelines over three engines on three
+ * streams each, driven by a few host threads (PIPSORT_BATCH_THREADS, default 3; lists of fewer than 8 loci: one), so that
+ * the uploads and preparation launches of the next loci and the read-back of the previous ones overlap the evaluation of
+ * the current ones.  loci[i] -> outs[i] (and n_configs[i], optional).  Stops at the first error.                    */
 int pipsort_posterior_exhaustive_batch(const pipsort_locus* loci, int32_t n_loci, int device, uint32_t flags, int c,
                                        const pipsort_outputs* outs, uint64_t* n_configs);
 
