@@ -33,6 +33,12 @@ typedef unsigned long long u64;
 #ifndef EXH_MINBLOCKS
 #define EXH_MINBLOCKS 3
 #endif
+#ifndef EXH_SKIP_SEL
+#define EXH_SKIP_SEL 0
+#endif
+#ifndef EXH_DEFER
+#define EXH_DEFER 1            // b cells of a step are folded over the warp at the top of the NEXT step (shuffle latency overlaps the exp chains)
+#endif
 #ifndef EXH_WARPS_PER_BLOCK
 #define EXH_WARPS_PER_BLOCK 4
 #endif
@@ -426,7 +432,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             remaining -= t_hi - t_lo;
             for (int t = t_lo; t < t_hi; t++) {
                 const int b = b0 + t;
-                if (pend_t >= 0) reduce_pending();
+                if (EXH_DEFER && pend_t >= 0) reduce_pending();
                 bool active = xin;
                 if (diag) {
                     active = active && x > b;
@@ -469,10 +475,15 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 if (active && !ok) slow_subset<J>(*Lg, a, b, x);      // rare, divergent, self-contained
                 {                                                   // a lane that is off contributes nothing on the fast path
                     const bool on = active && ok;
+#if EXH_SKIP_SEL
+                    if (__any_sync(0xffffffffu, !on))               // (most steps: every lane is on -- nothing to switch off)
+#endif
+                    {
 #pragma unroll
-                    for (int s = 0; s < 2; s++) {
-                        v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
-                        v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
+                        for (int s = 0; s < 2; s++) {
+                            v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
+                            v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
+                        }
                     }
                 }
 
@@ -521,6 +532,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                     double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
                     pend[0] = q0; pend[1] = q1; pend[2] = q2; pend[3] = q3; pend[4] = q4;
                     pend_t = t;
+                    if (!EXH_DEFER) { reduce_pending(); pend_t = -1; }
                 }
             }  // b window
             if (pend_t >= 0) reduce_pending();
