@@ -36,8 +36,10 @@ struct StudyDev {
     const double* u;     // z[i] / A[i]
     const double* e1m;   // E_s({i}) = exp(hd z^2/A) / sqrt(A) = e1m * 2^e1n
     const int* e1n;
-    const double* P;     // pair table, n x ldw: P[i][j] = E_s({i,j}) as a plain double, +inf when it leaves the fast range
-                         // (built on the first exhaustive run with c >= 2; nullptr before)
+    const double2* WP;   // LD + pair table of the exhaustive kernel, (n + 1) x ldp: WP[i][j] = { W[i][j], E_s({i,j}) as a plain
+                         // double, +inf when it leaves the fast range }; row n and column n are all zero (an absent SNP reads
+                         // W = 0, E = 0 without a predicate).  Built on the first exhaustive run with c >= 2; nullptr before.
+    int ldp;             // row length of WP (>= n + 1)
     int n;               // SNPs of this study that appear in the snp_map
     int ldw;
     double hd;           // d_s / 2

@@ -100,14 +100,16 @@ __global__ void __launch_bounds__(128) prepare_locus_kernel(PrepLocusArgs P) {
     }
 }
 
-struct PairTablesArgs { StudyDev st[2]; double* P[2]; };
-__global__ void __launch_bounds__(128) pair_tables_kernel(PairTablesArgs T) {   // pair_table_kernel for both studies
+struct PairTablesArgs { StudyDev st[2]; double2* WP[2]; };
+__global__ void __launch_bounds__(128) pair_tables_kernel(PairTablesArgs T) {   // WP table (common.cuh) of both studies
     const StudyDev& S = T.st[blockIdx.z];
-    double* __restrict__ P = T.P[blockIdx.z];
+    double2* __restrict__ WP = T.WP[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
-    if (j >= S.ldw || i >= S.n) return;
-    P[(size_t)i * S.ldw + j] = pair_table_entry(S, i, j);
+    if (j >= S.ldp || i > S.n) return;
+    double2 v = make_double2(0.0, 0.0);                  // row n, columns >= n: the absent SNP
+    if (i < S.n && j < S.n) v = make_double2(S.W[(size_t)i * S.ldw + j], pair_table_entry(S, i, j));
+    WP[(size_t)i * S.ldp + j] = v;
 }
 
 // ---- finalize: bins -> log-space results --------------------------------------------------------------
@@ -674,7 +676,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             const size_t nr = (size_t)lc->num_snps[s], n = e->orig[s].size(), ldw = (n + 3) & ~(size_t)3;
             nints += 2 * n + nr;
             est += (7 * nr + n * ldw) * 8;                                        // z upload, six vectors, W
-            if (lc->max_causal >= 2 && n <= 4096) est += n * ldw * 8;             // pair table (first exhaustive run)
+            if (lc->max_causal >= 2 && n <= 4096) est += (n + 1) * (ldw + 4) * 16 + 256;   // WP table (first exhaustive run)
             if (nr * nr * 8 <= ((size_t)4 << 20)) est += nr * nr * 8 + 256;        // small raw LD upload buffer
         }
         est += nints * 4;
@@ -1037,21 +1039,22 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     }
     // size classes 0..3: one launch of the register kernel (exhaustive.cuh); larger classes: generic kernel
     const int jreg = e->use_reg_kernel ? std::min(std::min(c, 3), e->U) : -1;
-    if (jreg >= 2 && !e->L.st[0].P) {
-        // first exhaustive run with pairs / triples: build the pair tables E_s{i,j} (n_s^2 doubles per study, once)
+    if (jreg >= 2 && !e->L.st[0].WP) {
+        // first exhaustive run with pairs / triples: build the tables { W_ij, E_s{i,j} } (16 (n_s + 1)^2 bytes per study, once)
         if (e->capturing) return fail(PIPSORT_E_ARG, "run the pass once before capturing it (the first run builds the pair tables)");
         PairTablesArgs pt;
         for (int s = 0; s < 2; s++) {
             StudyDev& st = e->L.st[s];
-            double* P = nullptr;
-            if ((rc = dev_alloc(e, &P, (size_t)std::max(st.n, 1) * std::max(st.ldw, 1)))) return rc;
+            double2* WP = nullptr;
+            st.ldp = (st.n + 1 + 1) & ~1;
+            if ((rc = dev_alloc(e, &WP, (size_t)(st.n + 1) * st.ldp))) return rc;
+            st.WP = WP;
             pt.st[s] = st;
-            pt.P[s] = P;
-            st.P = P;
+            pt.WP[s] = WP;
         }
-        const int nmax = std::max(pt.st[0].n, pt.st[1].n), lmax = std::max(pt.st[0].ldw, pt.st[1].ldw);
-        if (nmax > 0) {
-            dim3 grid((lmax + 127) / 128, nmax, 2);
+        const int nmax = std::max(pt.st[0].n, pt.st[1].n), lmax = std::max(pt.st[0].ldp, pt.st[1].ldp);
+        {
+            dim3 grid((lmax + 127) / 128, nmax + 1, 2);
             pair_tables_kernel<<<grid, 128, 0, e->stream>>>(pt);
             e->launches++;
         }

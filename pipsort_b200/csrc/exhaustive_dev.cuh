@@ -33,12 +33,6 @@ typedef unsigned long long u64;
 #ifndef EXH_MINBLOCKS
 #define EXH_MINBLOCKS 3
 #endif
-#ifndef EXH_SKIP_SEL
-#define EXH_SKIP_SEL 0
-#endif
-#ifndef EXH_DEFER
-#define EXH_DEFER 1            // b cells of a step are folded over the warp at the top of the NEXT step (shuffle latency overlaps the exp chains)
-#endif
 #ifndef EXH_WARPS_PER_BLOCK
 #define EXH_WARPS_PER_BLOCK 4
 #endif
@@ -245,17 +239,22 @@ struct WinStudy {
     double c2[EXH_BW];     // residual(b | a) / Schur(b | a)
     double v2[EXH_BW];     // E{b}   (0 when b is absent from the study)
     double v3[EXH_BW];     // E{a,b} (0 when a or b is absent)
-    int locb[EXH_BW];      // study-local index of b or -1
+    int row[EXH_BW + 1];   // row of b in the study's WP table; the all-zero row n when b is absent or past the window
 };
 struct WarpWin {
     WinStudy st[2];
     // b-cell accumulators of the window, flushed when the window is left.  Eight partial sums per (b, cell): a step's five
-    // b-cell values are folded over the warp only TWO shuffle levels deep (lanes l, l+8, l+16, l+24 -> lane l < 8) and the
-    // eight partial sums go on accumulating in shared memory; the last three levels are paid once per window, not once
-    // per step (the full butterfly was a quarter of the kernel's instructions).
+    // b-cell values are summed over the four lanes of a quad by a DMMA (exh_chunk) and the eight quads' sums go on
+    // accumulating here; the last three levels of the reduction are paid once per window, not once per step.
     double part[EXH_BW][5][EXH_PART];
+    int cum[EXH_BW + 1];     // cum[t] = number of states of the b's before step t (prefix sums: configuration count per segment)
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
+
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor core.  Lane l = 4 g + q holds A[g][q], B[q][g] and D[g][2q], D[g][2q+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 
 // One chunk of size class J (2 or 3): `remaining` warp-steps starting at step t_lo of the segment (a, window at b0,
 // x tile xt), continuing through the following tiles, windows and a's.  Warp-collective.
@@ -263,10 +262,13 @@ template <int J>
 __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P, int a, int b0, int xt, int t_lo, int remaining,
                                           WarpWin& win, const LocusDev* __restrict__ Lg, const int lane) {
     constexpr bool HAS_A = (J == 3);
+    constexpr int FAR = 1 << 24;
+    constexpr unsigned LIM_HI = (1023u + 450u) << 20;      // high word of FAST_LIMIT: e < 2^450  <=>  hi(e) < LIM_HI  (e >= 0)
     const AccDev& acc = L.acc;
     const int U = L.U;
     const int off = P.off, T1 = (U - 1 + off) >> 5;
     const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
+    const int grp = lane >> 2, quad = lane & 3;
     // chunk-lifetime accumulators (lane private, plain doubles): the scalars; a cells live as long as a does
     double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
     unsigned nconf = 0;
@@ -333,36 +335,46 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             __syncwarp();
             const int b = b0 + lane;
             const bool bv = lane < nb;
-            int okb = 1;
+            int okb = 1, hbs = 0;
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const StudyDev& S = L.st[s];
                 WinStudy& w = win.st[s];
                 const int lb = bv ? L.loc[s][b] : -1;
                 const bool hb = lb >= 0;
+                hbs += hb;
                 double Wab = 0.0, Ab = 1.0, zb = 0.0, v2 = 0.0, v3 = 0.0;
                 if (hb) {
                     Ab = S.A[lb]; zb = S.z[lb];
                     const int n = S.e1n[lb];
                     okb &= n < 440;
                     v2 = scale2(S.e1m[lb], min(n, 900));
-                    if (HAS_A && ha[s]) Wab = S.W[(size_t)la[s] * S.ldw + lb];
+                    if (HAS_A && ha[s]) {
+                        const double2 wp = S.WP[(size_t)la[s] * S.ldp + lb];     // { d Sigma[a][b], E{a,b} }
+                        Wab = wp.x; v3 = wp.y;
+                        okb &= v3 < FAST_LIMIT;
+                    }
                 }
                 // bordered step a -> {a,b}:  Schur = A_b - W_ab^2 / A_a,  residual = z_b - W_ab z_a / A_a
                 const double s22 = fma(-Wab * Wab, invAa[s], Ab);
                 const double r2 = fma(-Wab, ua[s], zb);
                 const double inv22 = 1.0 / s22;
-                if (HAS_A && ha[s] && hb) {
-                    bad |= !(s22 > 0.25);
-                    v3 = S.P[(size_t)la[s] * S.ldw + lb];                // E{a,b} from the pair table
-                    okb &= v3 < FAST_LIMIT;
-                }
+                if (HAS_A && ha[s] && hb) bad |= !(s22 > 0.25);
                 w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = r2 * inv22;
                 w.v2[lane] = v2; w.v3[lane] = v3;
-                w.locb[lane] = lb;
+                w.row[lane] = hb ? lb : S.n;
+                if (lane == 0) w.row[EXH_BW] = S.n;
             }
             if (!okb) { win.st[0].v2[lane] = 0.0; win.st[0].v3[lane] = 0.0; win.st[1].v2[lane] = 0.0; win.st[1].v3[lane] = 0.0; }
             win.ok[lane] = okb;
+            {   // prefix sums of the b's numbers of states
+                const int ns = hbs == 2 ? 3 : hbs;
+                int c = ns;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, c, o); if (lane >= o) c += v; }
+                win.cum[lane + 1] = c;
+                if (lane == 0) win.cum[0] = 0;
+            }
 #pragma unroll
             for (int k = 0; k < 5 * EXH_PART; k++) (&win.part[0][0][0])[k * 32 + lane] = 0.0;
             __syncwarp();
@@ -372,118 +384,117 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             const int x = xt * 32 + lane - off;
             const bool xin = x >= 0;                                     // (the top tile ends exactly at U - 1)
             // ---- per-tile lane values of x: masks {x} (4) and {a,x} (5) ----------------------------------
-            int hx[2], lx[2];
-            double px[2], cx[2], rx[2], Ax[2], zx[2], v4[2], v5[2];
+            int hx[2];
+            const double2* wpx[2];                                       // column of x in the study's WP table (the zero column when absent)
+            double px[2], cx[2], rx[2], v4[2], v5[2];
             bool okX = true;
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const StudyDev& S = L.st[s];
-                lx[s] = xin ? L.loc[s][x] : -1;
-                hx[s] = lx[s] >= 0;
-                double Wax = 0.0;
-                Ax[s] = 1.0; zx[s] = 0.0; v4[s] = 0.0; v5[s] = 0.0;
+                const int lx = xin ? L.loc[s][x] : -1;
+                hx[s] = lx >= 0;
+                double Wax = 0.0, Ax = 1.0, zx = 0.0;
+                v4[s] = 0.0; v5[s] = 0.0;
+                wpx[s] = S.WP + (hx[s] ? lx : S.n);
                 if (hx[s]) {
-                    Ax[s] = S.A[lx[s]]; zx[s] = S.z[lx[s]];
-                    const int n = S.e1n[lx[s]];
+                    Ax = S.A[lx]; zx = S.z[lx];
+                    const int n = S.e1n[lx];
                     okX = okX && n < 440;
-                    v4[s] = scale2(S.e1m[lx[s]], min(n, 900));
-                    if (HAS_A && ha[s]) Wax = S.W[(size_t)la[s] * S.ldw + lx[s]];
+                    v4[s] = scale2(S.e1m[lx], min(n, 900));
+                    if (HAS_A && ha[s]) {
+                        const double2 wp = wpx[s][(size_t)la[s] * S.ldp];          // { d Sigma[a][x], E{a,x} }
+                        Wax = wp.x; v5[s] = wp.y;
+                        okX = okX && v5[s] < FAST_LIMIT;
+                    }
                 }
                 px[s] = Wax * invAa[s];
-                cx[s] = fma(-Wax, px[s], Ax[s]);
-                rx[s] = fma(-Wax, ua[s], zx[s]);
-                if (HAS_A && ha[s] && hx[s]) {
-                    bad |= !(cx[s] > 0.25);
-                    v5[s] = S.P[(size_t)la[s] * S.ldw + lx[s]];          // E{a,x}
-                    okX = okX && v5[s] < FAST_LIMIT;
-                }
+                cx[s] = fma(-Wax, px[s], Ax);
+                rx[s] = fma(-Wax, ua[s], zx);
+                if (HAS_A && ha[s] && hx[s]) bad |= !(cx[s] > 0.25);
             }
             okX = okX && okA;
             if (!okX) { v4[0] = 0.0; v4[1] = 0.0; v5[0] = 0.0; v5[1] = 0.0; }
             const int nstates_x = hx[0] && hx[1] ? 3 : (hx[0] || hx[1] ? 1 : 0);
-            double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            const bool diag = P.partial || (b0 + nb - 1 + off >= xt * 32);   // some lane may be inactive at some step
-            double wnext[2], pnext[2];                                   // W[b][x], E{b,x} of the NEXT step (software prefetch)
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const int lb = win.st[s].locb[t_lo];
-                const bool h = lb >= 0 && hx[s];
-                const size_t o = h ? (size_t)lb * L.st[s].ldw + lx[s] : 0;
-                wnext[s] = h ? L.st[s].W[o] : 0.0;
-                pnext[s] = h ? L.st[s].P[o] : 0.0;
-            }
-
-            // b cells of the PREVIOUS step: their warp reduction is issued at the top of the next step so that its
-            // shuffle latency overlaps the exp / rsqrt chains (software pipelining)
-            double pend[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            int pend_t = -1;
-            auto reduce_pending = [&]() {
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    double r = pend[k];
-                    r += __shfl_xor_sync(0xffffffffu, r, 16);
-                    r += __shfl_xor_sync(0xffffffffu, r, 8);
-                    if (lane < EXH_PART) win.part[pend_t][k][lane] += r;
+            // ---- the steps [tA, tB) of this segment in which the lane's subset {a, b0 + t, x} exists and lies in the rank range
+            // (lexicographic bounds: for fixed a and x the admissible b's are an interval)
+            int tA = 0, tB = xin ? x - b0 : 0;                           // b < x
+            if (P.partial) {
+                int bmin, bmax;                                          // b in [bmin, bmax)
+                if (HAS_A) {
+                    bmin = a > P.lo[0] ? -FAR : (a == P.lo[0] ? (x >= P.lo[2] ? P.lo[1] : P.lo[1] + 1) : FAR);
+                    bmax = a < P.hi[0] ? FAR : (a == P.hi[0] ? (x < P.hi[2] ? P.hi[1] + 1 : P.hi[1]) : -FAR);
+                } else {
+                    bmin = x >= P.lo[1] ? P.lo[0] : P.lo[0] + 1;
+                    bmax = x < P.hi[1] ? P.hi[0] + 1 : P.hi[0];
                 }
+                tA = max(tA, bmin - b0);
+                tB = min(tB, bmax - b0);
+            }
+            double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double cacc[5][2];                                           // b cells: D fragments of the quad sums, column = step & 7
+#pragma unroll
+            for (int k = 0; k < 5; k++) { cacc[k][0] = 0.0; cacc[k][1] = 0.0; }
+            auto flush_c = [&](int tb) {                                 // lane (grp, quad) holds the sums of quad `grp` for steps tb + 2 quad, + 1
+#pragma unroll
+                for (int k = 0; k < 5; k++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        win.part[tb + 2 * quad + i][k][(grp + 2 * quad) & (EXH_PART - 1)] += cacc[k][i];
+                        cacc[k][i] = 0.0;
+                    }
             };
             // steps of this segment: the b's of the window that have an x of this tile beyond them, from t_lo on, as
             // far as the chunk reaches
             const int t_hi = min(min(nb, xt * 32 + 31 - off - b0), t_lo + remaining);
             remaining -= t_hi - t_lo;
+            {   // expanded configurations of the lane's subsets in this segment (the reference's mycount)
+                const int c_lo = max(tA, t_lo), c_hi = min(tB, t_hi);
+                if (c_hi > c_lo) nconf += (unsigned)(nstates_a * nstates_x * (win.cum[c_hi] - win.cum[c_lo]));
+            }
+            const size_t ldp0 = L.st[0].ldp, ldp1 = L.st[1].ldp;
+            double2 nxt[2];                                              // { W[b][x], E{b,x} } of the NEXT step (software prefetch)
+            nxt[0] = wpx[0][(size_t)win.st[0].row[t_lo] * ldp0];
+            nxt[1] = wpx[1][(size_t)win.st[1].row[t_lo] * ldp1];
+            unsigned slowmask = 0;
             for (int t = t_lo; t < t_hi; t++) {
-                const int b = b0 + t;
-                if (EXH_DEFER && pend_t >= 0) reduce_pending();
-                bool active = xin;
-                if (diag) {
-                    active = active && x > b;
-                    if (P.partial) active = active && lex_in_range<J>(P, a, b, x);
-                }
+                const bool active = t >= tA && t < tB;
                 double v[2][8];
-                int hb[2];
-                bool ok = okX && win.ok[t];
+                unsigned okbits = 0;                                     // any set bit: some E is outside the fast range / a Schur complement is not >= 1/4
                 // Branch-free on purpose: both studies' chains (bordered Cholesky step -> rsqrt -> exp) sit in ONE basic
-                // block so that the compiler interleaves them.  Absent SNPs are "virtual" (W = 0, A = 1, z = 0, E = 0): the
-                // arithmetic stays finite and the zero base E{a,b} or the final select switch the expansion off.
+                // block so that the compiler interleaves them.  Absent SNPs are "virtual" (W = 0, A = 1, z = 0, E = 0: the zero
+                // row / column of the WP table): the arithmetic stays finite and the zero base E{a,b} or the final select
+                // switch the expansion off.
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     const StudyDev& S = L.st[s];
                     const WinStudy& w = win.st[s];
-                    hb[s] = w.locb[t] >= 0;
-                    const double Wbx = wnext[s];
-                    const double e6 = pnext[s];                          // E{b,x} from the pair table (0 when b or x is absent)
-                    {
-                        const int lbn = w.locb[min(t + 1, nb - 1)];     // next step's W[b][x], E{b,x} (software prefetch)
-                        const bool h = lbn >= 0 && hx[s];
-                        const size_t o = h ? (size_t)lbn * S.ldw + lx[s] : 0;
-                        wnext[s] = h ? S.W[o] : 0.0;
-                        pnext[s] = h ? S.P[o] : 0.0;
-                    }
+                    const double Wbx = nxt[s].x;
+                    const double e6 = nxt[s].y;                          // E{b,x} from the pair table (0 when b or x is absent)
+                    nxt[s] = wpx[s][(size_t)w.row[t + 1] * (s ? ldp1 : ldp0)];
                     double e7 = 0.0;
                     if (HAS_A) {
                         const double tt = fma(-w.Wab[t], px[s], Wbx);
                         const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
                         const double r7 = fma(-tt, w.c2[t], rx[s]);
-                        const double e = extend_fast(w.v3[t], S.hd, r7, s7, bad);   // v3 = 0 when a or b is absent
+                        const double rs = rsqrt_fast(s7);
+                        const double uu = r7 * rs;
+                        const double e = w.v3[t] * (exp_pos(S.hd * (uu * uu)) * rs);   // v3 = 0 when a or b is absent
                         e7 = hx[s] ? e : 0.0;
+                        okbits |= (unsigned)(__double2hiint(s7) < 0x3fd00000);     // (signed: negative values fail too; NaN shows up in e)
+                        okbits |= (unsigned)((unsigned)__double2hiint(e) >= LIM_HI);
                     }
-                    ok = ok && (e6 < FAST_LIMIT) && (e7 < FAST_LIMIT);
+                    okbits |= (unsigned)((unsigned)__double2hiint(e6) >= LIM_HI);
                     v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
                     v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6; v[s][7] = e7;
                 }
-                const int nstates_b = hb[0] && hb[1] ? 3 : (hb[0] || hb[1] ? 1 : 0);
-                if (active) nconf += (unsigned)(nstates_a * nstates_b * nstates_x);
-                if (active && !ok) slow_subset<J>(*Lg, a, b, x);      // rare, divergent, self-contained
+                const bool ok = okX && win.ok[t] && okbits == 0;
+                if (active && !ok) slowmask |= 1u << t;             // rare: re-evaluated after the loop (slow_subset)
                 {                                                   // a lane that is off contributes nothing on the fast path
                     const bool on = active && ok;
-#if EXH_SKIP_SEL
-                    if (__any_sync(0xffffffffu, !on))               // (most steps: every lane is on -- nothing to switch off)
-#endif
-                    {
 #pragma unroll
-                        for (int s = 0; s < 2; s++) {
-                            v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
-                            v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
-                        }
+                    for (int s = 0; s < 2; s++) {
+                        v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
+                        v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
                     }
                 }
 
@@ -526,22 +537,34 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 }
                 accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
                 accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
-                {   // b cells: warp-reduced one step later (reduce_pending) into the shared-memory window accumulators
+                {   // b cells: the five values of the step are summed over the lanes of each quad by a DMMA whose B operand
+                    // routes the sums into column (t & 7) of the accumulator fragments; the fragments go to the shared-memory
+                    // window accumulators every eight steps
                     double (&g)[3][3] = G[1];
-                    double q0 = wsumX(g[0], false), q1 = wsumX(g[1], false), q2 = wsumX(g[2], true);   // X1 X2 X3
-                    double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
-                    pend[0] = q0; pend[1] = q1; pend[2] = q2; pend[3] = q3; pend[4] = q4;
-                    pend_t = t;
-                    if (!EXH_DEFER) { reduce_pending(); pend_t = -1; }
+                    const double q0 = wsumX(g[0], false), q1 = wsumX(g[1], false), q2 = wsumX(g[2], true);   // X1 X2 X3
+                    const double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
+                    const double sel = grp == (t & 7) ? 1.0 : 0.0;
+                    dmma884(cacc[0][0], cacc[0][1], q0, sel);
+                    dmma884(cacc[1][0], cacc[1][1], q1, sel);
+                    dmma884(cacc[2][0], cacc[2][1], q2, sel);
+                    dmma884(cacc[3][0], cacc[3][1], q3, sel);
+                    dmma884(cacc[4][0], cacc[4][1], q4, sel);
+                    if ((t & 7) == 7) flush_c(t - 7);
                 }
             }  // b window
-            if (pend_t >= 0) reduce_pending();
+            if (t_hi > t_lo && (t_hi & 7) != 0) flush_c((t_hi - 1) & ~7);
 
             accT += (accX[X1] + accX[X2]) + accX[X3];   // every expansion is in exactly one x cell: the total, once per tile
             if (xin) {   // flush the x cells of this tile
 #pragma unroll
                 for (int k = 0; k < 5; k++) bin_add(acc, k, x, accX[k], 0);
             }
+            while (slowmask) {                          // rare, divergent, self-contained
+                const int t = __ffs(slowmask) - 1;
+                slowmask &= slowmask - 1;
+                slow_subset<J>(*Lg, a, b0 + t, x);
+            }
+            __syncwarp();
         }  // segment
         // ---- advance: next tile, else next window, else next a --------------------------------------------------------
         if (remaining > 0) {
