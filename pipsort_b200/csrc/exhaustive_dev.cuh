@@ -38,7 +38,8 @@ typedef unsigned long long u64;
 #endif
 constexpr int EXH_WARPS = EXH_WARPS_PER_BLOCK;   // warps per block
 constexpr int EXH_BW = 32;            // max b-window
-constexpr int EXH_PART = 8;           // partial sums kept per b-cell (lanes that survive two shuffle levels)
+constexpr int EXH_STG = 6;            // steps whose b-cell values are staged in shared memory before their rows are summed (5 x 6 rows <= 32 lanes)
+constexpr int EXH_STG_LD = 34;        // row length of the staging area in doubles (32 lanes + padding: 16-byte loads of a row stay conflict free)
 constexpr int PEN = -4096;            // exponent penalty that switches an expansion off (slow path)
 constexpr double FAST_LIMIT = 0x1p+450;
 
@@ -236,25 +237,22 @@ __device__ __noinline__ void slow_subset(const LocusDev& L, int a, int b, int x)
 struct WinStudy {
     double Wab[EXH_BW];    // d Sigma[a][b]                      (0 when a or b is absent from the study)
     double inv22[EXH_BW];  // 1 / Schur(b | a)
-    double c2[EXH_BW];     // residual(b | a) / Schur(b | a)
+    double c2[EXH_BW];     // sqrt(d/2) residual(b | a) / Schur(b | a)
     double v2[EXH_BW];     // E{b}   (0 when b is absent from the study)
     double v3[EXH_BW];     // E{a,b} (0 when a or b is absent)
     int row[EXH_BW + 1];   // row of b in the study's WP table; the all-zero row n when b is absent or past the window
 };
-struct WarpWin {
+struct alignas(16) WarpWin {
+    // staging area of the b-cell values: a step writes its five values lane by lane into rows (slot, cell); every EXH_STG
+    // steps lane 5 slot + cell sums its row (16 loads of 16 bytes) into `part` -- no shuffles, and one addition per value
+    // instead of a butterfly per step.  (First member: the rows are read as 16-byte words.)
+    double stage[EXH_STG * 5][EXH_STG_LD];
     WinStudy st[2];
-    // b-cell accumulators of the window, flushed when the window is left.  Eight partial sums per (b, cell): a step's five
-    // b-cell values are summed over the four lanes of a quad by a DMMA (exh_chunk) and the eight quads' sums go on
-    // accumulating here; the last three levels of the reduction are paid once per window, not once per step.
-    double part[EXH_BW][5][EXH_PART];
+    // b-cell accumulators of the window, flushed when the window is left
+    double part[EXH_BW][5];
     int cum[EXH_BW + 1];     // cum[t] = number of states of the b's before step t (prefix sums: configuration count per segment)
     int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
 };
-
-// D(8x8) += A(8x4) B(4x8) on the FP64 tensor core.  Lane l = 4 g + q holds A[g][q], B[q][g] and D[g][2q], D[g][2q+1].
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // One chunk of size class J (2 or 3): `remaining` warp-steps starting at step t_lo of the segment (a, window at b0,
 // x tile xt), continuing through the following tiles, windows and a's.  Warp-collective.
@@ -268,9 +266,15 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     const int U = L.U;
     const int off = P.off, T1 = (U - 1 + off) >> 5;
     const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
-    const int grp = lane >> 2, quad = lane & 3;
+    const double shd[2] = {sqrt(L.st[0].hd), sqrt(L.st[1].hd)};   // sqrt(d/2): folded into the residuals, so that the exponent is a plain square
+    auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
+        return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
+    };
+    auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
     // chunk-lifetime accumulators (lane private, plain doubles): the scalars; a cells live as long as a does
-    double accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+    // GA[state][a'] = the a cells, UNWEIGHTED: the products of the expansions accumulate straight into them step after step;
+    // the prior weights are applied when a is left
+    double GA[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
     unsigned nconf = 0;
     int bad = 0;
     int ha[2] = {0, 0}, la[2] = {-1, -1};
@@ -278,17 +282,26 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     bool okA = true;
     int nstates_a = 1, nb = 0;
     bool new_a = true, new_win = true;
+    auto cells_of = [&](const double (&g)[3][3], double (&c)[5]) {   // X1 X2 X3 YS YN from the unweighted sums
+        c[X1] = wsumX(g[0], false); c[X2] = wsumX(g[1], false); c[X3] = wsumX(g[2], true);
+        c[YS] = sumY(g[2]);
+        c[YN] = sumY(g[0]) + sumY(g[1]);
+    };
     auto flush_a = [&]() {        // a cells of the a that is being left: five sums over the warp, one atomic each
         if (HAS_A) {
-            double mine = 0.0;
+            double accA[5], mine = 0.0;
+            cells_of(GA, accA);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 double r = accA[k];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
                 if (lane == k) mine = r;
-                accA[k] = 0.0;
             }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) GA[i][q] = 0.0;
             if (lane < 5) bin_add(acc, lane, a, mine, 0);
         }
     };
@@ -296,12 +309,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
         __syncwarp();
         if (lane < nb) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                double sm = 0.0;
-#pragma unroll
-                for (int q = 0; q < EXH_PART; q++) sm += win.part[lane][k][(q + lane) & (EXH_PART - 1)];   // (rotated: fewer bank conflicts)
-                bin_add(acc, k, b0 + lane, sm, 0);
-            }
+            for (int k = 0; k < 5; k++) bin_add(acc, k, b0 + lane, win.part[lane][k], 0);
         }
     };
     while (remaining > 0) {
@@ -360,7 +368,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 const double r2 = fma(-Wab, ua[s], zb);
                 const double inv22 = 1.0 / s22;
                 if (HAS_A && ha[s] && hb) bad |= !(s22 > 0.25);
-                w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = r2 * inv22;
+                w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = shd[s] * (r2 * inv22);
                 w.v2[lane] = v2; w.v3[lane] = v3;
                 w.row[lane] = hb ? lb : S.n;
                 if (lane == 0) w.row[EXH_BW] = S.n;
@@ -376,7 +384,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 if (lane == 0) win.cum[0] = 0;
             }
 #pragma unroll
-            for (int k = 0; k < 5 * EXH_PART; k++) (&win.part[0][0][0])[k * 32 + lane] = 0.0;
+            for (int k = 0; k < 5; k++) (&win.part[0][0])[k * 32 + lane] = 0.0;
             __syncwarp();
         }
 
@@ -409,7 +417,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 }
                 px[s] = Wax * invAa[s];
                 cx[s] = fma(-Wax, px[s], Ax);
-                rx[s] = fma(-Wax, ua[s], zx);
+                rx[s] = shd[s] * fma(-Wax, ua[s], zx);
                 if (HAS_A && ha[s] && hx[s]) bad |= !(cx[s] > 0.25);
             }
             okX = okX && okA;
@@ -430,19 +438,23 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 tA = max(tA, bmin - b0);
                 tB = min(tB, bmax - b0);
             }
-            double accX[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            double cacc[5][2];                                           // b cells: D fragments of the quad sums, column = step & 7
+            double GX[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // the x cells of the tile, unweighted (like GA)
+            // b cells: `ns` steps starting at step tb are staged; lane 5 slot + cell sums row (slot, cell) over the 32 lanes
+            auto flush_stage = [&](int tb, int ns) {
+                __syncwarp();
+                if (lane < 5 * ns) {
+                    const double2* row = reinterpret_cast<const double2*>(&win.stage[lane][0]);
+                    double2 s0 = row[0], s1 = row[1];
 #pragma unroll
-            for (int k = 0; k < 5; k++) { cacc[k][0] = 0.0; cacc[k][1] = 0.0; }
-            auto flush_c = [&](int tb) {                                 // lane (grp, quad) holds the sums of quad `grp` for steps tb + 2 quad, + 1
-#pragma unroll
-                for (int k = 0; k < 5; k++)
-#pragma unroll
-                    for (int i = 0; i < 2; i++) {
-                        win.part[tb + 2 * quad + i][k][(grp + 2 * quad) & (EXH_PART - 1)] += cacc[k][i];
-                        cacc[k][i] = 0.0;
+                    for (int j = 2; j < 16; j += 2) {
+                        const double2 u0 = row[j], u1 = row[j + 1];
+                        s0.x += u0.x; s0.y += u0.y; s1.x += u1.x; s1.y += u1.y;
                     }
+                    win.part[tb + lane / 5][lane % 5] += (s0.x + s0.y) + (s1.x + s1.y);
+                }
+                __syncwarp();
             };
+            int slot = 0;                                                // staged steps
             // steps of this segment: the b's of the window that have an x of this tile beyond them, from t_lo on, as
             // far as the chunk reaches
             const int t_hi = min(min(nb, xt * 32 + 31 - off - b0), t_lo + remaining);
@@ -459,35 +471,59 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             for (int t = t_lo; t < t_hi; t++) {
                 const bool active = t >= tA && t < tB;
                 double v[2][8];
-                unsigned okbits = 0;                                     // any set bit: some E is outside the fast range / a Schur complement is not >= 1/4
+                unsigned emax = 0;                                       // largest high word of the step's E's (non-negative doubles order like integers)
+                int smin = 0x7fffffff;                                   // smallest high word of the Schur complements
                 // Branch-free on purpose: both studies' chains (bordered Cholesky step -> rsqrt -> exp) sit in ONE basic
                 // block so that the compiler interleaves them.  Absent SNPs are "virtual" (W = 0, A = 1, z = 0, E = 0: the zero
                 // row / column of the WP table): the arithmetic stays finite and the zero base E{a,b} or the final select
                 // switch the expansion off.
+                // (written stage by stage over both studies, see xexp_pair)
+                double Wbx[2], e6[2], e7[2] = {0.0, 0.0};
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
-                    const StudyDev& S = L.st[s];
-                    const WinStudy& w = win.st[s];
-                    const double Wbx = nxt[s].x;
-                    const double e6 = nxt[s].y;                          // E{b,x} from the pair table (0 when b or x is absent)
-                    nxt[s] = wpx[s][(size_t)w.row[t + 1] * (s ? ldp1 : ldp0)];
-                    double e7 = 0.0;
-                    if (HAS_A) {
-                        const double tt = fma(-w.Wab[t], px[s], Wbx);
-                        const double s7 = fma(-tt * tt, w.inv22[t], cx[s]);
-                        const double r7 = fma(-tt, w.c2[t], rx[s]);
-                        const double rs = rsqrt_fast(s7);
-                        const double uu = r7 * rs;
-                        const double e = w.v3[t] * (exp_pos(S.hd * (uu * uu)) * rs);   // v3 = 0 when a or b is absent
-                        e7 = hx[s] ? e : 0.0;
-                        okbits |= (unsigned)(__double2hiint(s7) < 0x3fd00000);     // (signed: negative values fail too; NaN shows up in e)
-                        okbits |= (unsigned)((unsigned)__double2hiint(e) >= LIM_HI);
-                    }
-                    okbits |= (unsigned)((unsigned)__double2hiint(e6) >= LIM_HI);
-                    v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
-                    v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6; v[s][7] = e7;
+                    Wbx[s] = nxt[s].x;
+                    e6[s] = nxt[s].y;                                    // E{b,x} from the pair table (0 when b or x is absent)
+                    nxt[s] = wpx[s][(size_t)win.st[s].row[t + 1] * (s ? ldp1 : ldp0)];
                 }
-                const bool ok = okX && win.ok[t] && okbits == 0;
+                if (HAS_A) {
+                    double tt[2], s7[2], r7[2], y0[2], ee[2], rs[2], uu[2], arg[2], em[2];
+                    int en[2];
+#pragma unroll
+                    for (int s = 0; s < 2; s++) tt[s] = fma(-win.st[s].Wab[t], px[s], Wbx[s]);
+#pragma unroll
+                    for (int s = 0; s < 2; s++) s7[s] = fma(-tt[s] * tt[s], win.st[s].inv22[t], cx[s]);
+#pragma unroll
+                    for (int s = 0; s < 2; s++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[s]) : "d"(s7[s]));
+#pragma unroll
+                    for (int s = 0; s < 2; s++) r7[s] = fma(-tt[s], win.st[s].c2[t], rx[s]);       // sqrt(d/2) x the residual
+#pragma unroll
+                    for (int s = 0; s < 2; s++) ee[s] = fma(s7[s], -(y0[s] * y0[s]), 1.0);        // rsqrt_fast, both studies
+#pragma unroll
+                    for (int s = 0; s < 2; s++) rs[s] = fma(fma(ee[s], 0.375, 0.5), y0[s] * ee[s], y0[s]);
+#pragma unroll
+                    for (int s = 0; s < 2; s++) uu[s] = r7[s] * rs[s];
+#pragma unroll
+                    for (int s = 0; s < 2; s++) arg[s] = uu[s] * uu[s];
+                    xexp_pair(arg, em, en);
+#pragma unroll
+                    for (int s = 0; s < 2; s++) {
+                        en[s] = min(en[s], 1000);
+                        const double ex = __hiloint2double(__double2hiint(em[s]) + (en[s] << 20), __double2loint(em[s]));
+                        const double e = win.st[s].v3[t] * (ex * rs[s]);                            // v3 = 0 when a or b is absent
+                        e7[s] = hx[s] ? e : 0.0;
+                        smin = min(smin, __double2hiint(s7[s]));                  // (signed: negative values fail too; NaN shows up in e)
+                        emax = max(emax, (unsigned)__double2hiint(e));
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const WinStudy& w = win.st[s];
+                    emax = max(emax, (unsigned)__double2hiint(e6[s]));
+                    v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
+                    v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6[s]; v[s][7] = e7[s];
+                }
+                // fast path: every E below 2^450 (as unsigned high words: negative or NaN fails), every Schur complement >= 1/4
+                const bool ok = okX && win.ok[t] && emax < LIM_HI && smin >= 0x3fd00000;
                 if (active && !ok) slowmask |= 1u << t;             // rare: re-evaluated after the loop (slow_subset)
                 {                                                   // a lane that is off contributes nothing on the fast path
                     const bool on = active && ok;
@@ -498,19 +534,10 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                     }
                 }
 
-                // ---- cells: g[state][a'] = sum over the expansions with one SNP in that state, a' = number of
-                // OTHER SNPs causal in both studies.
-                auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
-                    return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
-                };
-                auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
-                double G[3][3][3];
-#pragma unroll
-                for (int i = 0; i < 3; i++)
-#pragma unroll
-                    for (int q = 0; q < 3; q++)
-#pragma unroll
-                        for (int r = 0; r < 3; r++) G[i][q][r] = 0.0;
+                // ---- cells: G[state][a'] = sum over the expansions with one SNP in that state, a' = number of OTHER SNPs causal
+                // in both studies.  The x cells (GX) and the a cells (GA) go on accumulating over the steps of the tile / of a:
+                // the 27 products are all the arithmetic they cost per step.  The b cells of the step get their prior weights here.
+                double GB[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
                 for (int tx = 0; tx < 3; tx++)
 #pragma unroll
@@ -520,40 +547,24 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                             const int m0 = (HAS_A && in0(ta) ? 1 : 0) | (in0(tb) ? 2 : 0) | (in0(tx) ? 4 : 0);
                             const int m1 = (HAS_A && in1(ta) ? 1 : 0) | (in1(tb) ? 2 : 0) | (in1(tx) ? 4 : 0);
                             const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
-                            G[2][tx][ac - (tx == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[2][tx][ac - (tx == 2 ? 1 : 0)]);
-                            G[1][tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[1][tb][ac - (tb == 2 ? 1 : 0)]);
-                            if (HAS_A) G[0][ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], G[0][ta][ac - (ta == 2 ? 1 : 0)]);
+                            GX[tx][ac - (tx == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GX[tx][ac - (tx == 2 ? 1 : 0)]);
+                            GB[tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GB[tb][ac - (tb == 2 ? 1 : 0)]);
+                            if (HAS_A) GA[ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GA[ta][ac - (ta == 2 ? 1 : 0)]);
                         }
-                {
-                    const double x1 = wsumX(G[2][0], false), x2 = wsumX(G[2][1], false), x3 = wsumX(G[2][2], true);
-                    accX[X1] += x1; accX[X2] += x2; accX[X3] += x3;
-                    accX[YS] += sumY(G[2][2]);
-                    accX[YN] += sumY(G[2][0]) + sumY(G[2][1]);
-                }
-                if (HAS_A) {
-                    accA[X1] += wsumX(G[0][0], false); accA[X2] += wsumX(G[0][1], false); accA[X3] += wsumX(G[0][2], true);
-                    accA[YS] += sumY(G[0][2]);
-                    accA[YN] += sumY(G[0][0]) + sumY(G[0][1]);
-                }
                 accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
                 accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
-                {   // b cells: the five values of the step are summed over the lanes of each quad by a DMMA whose B operand
-                    // routes the sums into column (t & 7) of the accumulator fragments; the fragments go to the shared-memory
-                    // window accumulators every eight steps
-                    double (&g)[3][3] = G[1];
-                    const double q0 = wsumX(g[0], false), q1 = wsumX(g[1], false), q2 = wsumX(g[2], true);   // X1 X2 X3
-                    const double q3 = sumY(g[2]), q4 = sumY(g[0]) + sumY(g[1]);                              // YS YN
-                    const double sel = grp == (t & 7) ? 1.0 : 0.0;
-                    dmma884(cacc[0][0], cacc[0][1], q0, sel);
-                    dmma884(cacc[1][0], cacc[1][1], q1, sel);
-                    dmma884(cacc[2][0], cacc[2][1], q2, sel);
-                    dmma884(cacc[3][0], cacc[3][1], q3, sel);
-                    dmma884(cacc[4][0], cacc[4][1], q4, sel);
-                    if ((t & 7) == 7) flush_c(t - 7);
+                {   // b cells: staged lane by lane; the rows are summed every EXH_STG steps
+                    double q[5];
+                    cells_of(GB, q);
+#pragma unroll
+                    for (int k = 0; k < 5; k++) win.stage[slot * 5 + k][lane] = q[k];
+                    if (++slot == EXH_STG) { flush_stage(t + 1 - EXH_STG, EXH_STG); slot = 0; }
                 }
             }  // b window
-            if (t_hi > t_lo && (t_hi & 7) != 0) flush_c((t_hi - 1) & ~7);
+            if (slot) flush_stage(t_hi - slot, slot);
 
+            double accX[5];
+            cells_of(GX, accX);
             accT += (accX[X1] + accX[X2]) + accX[X3];   // every expansion is in exactly one x cell: the total, once per tile
             if (xin) {   // flush the x cells of this tile
 #pragma unroll
@@ -588,7 +599,8 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     // ---- end of the chunk: b window, a cells, scalars ---------------------------------------------------------------
     flush_window();
     {
-        double r[8];
+        double r[8], accA[5];
+        cells_of(GA, accA);
 #pragma unroll
         for (int k = 0; k < 5; k++) r[k] = accA[k];
         r[5] = accT; r[6] = accNC0; r[7] = accNC1;
@@ -695,6 +707,7 @@ exhaustive_all_kernel(LocusDev L, ExhAll A, const LocusDev* __restrict__ Lg) {
     }
 }
 
+static_assert(sizeof(WarpWin) % 16 == 0 && (EXH_STG_LD * 8) % 16 == 0, "16-byte loads of the staging rows");
 constexpr size_t EXH_SMEM_BYTES = sizeof(WarpWin) * EXH_WARPS;
 
 }  // namespace pipsort

@@ -95,6 +95,44 @@ __device__ __forceinline__ void xexp(double t, double& m, int& n) {
 #endif
 }
 
+// two independent xexp evaluations written stage by stage: the scheduler keeps the order it is given as the tie-breaker,
+// and one evaluation after the other would leave every dependent operation waiting out its full latency
+__device__ __forceinline__ void xexp_pair(const double (&t)[2], double (&m)[2], int (&n)[2]) {
+    const double LOG2E = 1.4426950408889634, LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double MAGIC = 6755399441055744.0;
+    double tmp[2], kf[2], r[2], r2[2], a[2][7], r4[2], b[2][3], r8[2], d[2][2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) tmp[s] = fma(t[s], LOG2E, MAGIC);
+#pragma unroll
+    for (int s = 0; s < 2; s++) { n[s] = __double2loint(tmp[s]); kf[s] = tmp[s] - MAGIC; }
+#pragma unroll
+    for (int s = 0; s < 2; s++) r[s] = fma(-kf[s], LN2_HI, t[s]);
+#pragma unroll
+    for (int s = 0; s < 2; s++) r[s] = fma(-kf[s], LN2_LO, r[s]);
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        r2[s] = r[s] * r[s];
+        a[s][0] = 1.0 + r[s];
+#pragma unroll
+        for (int i = 1; i < 7; i++) a[s][i] = fma(XEXP_C[12 - 2 * i], r[s], XEXP_C[13 - 2 * i]);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        r4[s] = r2[s] * r2[s];
+        b[s][0] = fma(a[s][1], r2[s], a[s][0]);
+        b[s][1] = fma(a[s][3], r2[s], a[s][2]);
+        b[s][2] = fma(a[s][5], r2[s], a[s][4]);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        r8[s] = r4[s] * r4[s];
+        d[s][0] = fma(b[s][1], r4[s], b[s][0]);
+        d[s][1] = fma(a[s][6], r4[s], b[s][2]);
+    }
+#pragma unroll
+    for (int s = 0; s < 2; s++) m[s] = fma(d[s][1], r8[s], d[s][0]);
+}
+
 // natural log of an accumulator; caller handles M == 0 (empty)
 __device__ __forceinline__ double xlog(const XAcc& a) { return log(a.M) + (double)a.N * 0.6931471805599453094; }
 
