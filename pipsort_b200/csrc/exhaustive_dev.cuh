@@ -23,6 +23,8 @@
 // then 32-wide tiles of x, then the b's of the window); a CHUNK is a contiguous run of it, handed out by an atomic counter.
 // The union-subset rank range [r_begin, r_end) of the C-ABI is honoured by a lexicographic predicate per lane.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "exh_plan.h"
 
@@ -281,7 +283,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     double invAa[2] = {1.0, 1.0}, ua[2] = {0.0, 0.0}, v1[2] = {0.0, 0.0};
     bool okA = true;
     int nstates_a = 1, nb = 0;
-    bool new_a = true, new_win = true;
+    bool new_a = true, new_win = true, win_has1 = true;           // win_has1: some b of the window is in study 1
     auto cells_of = [&](const double (&g)[3][3], double (&c)[5]) {   // X1 X2 X3 YS YN from the unweighted sums
         c[X1] = wsumX(g[0], false); c[X2] = wsumX(g[1], false); c[X3] = wsumX(g[2], true);
         c[YS] = sumY(g[2]);
@@ -375,6 +377,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             }
             if (!okb) { win.st[0].v2[lane] = 0.0; win.st[0].v3[lane] = 0.0; win.st[1].v2[lane] = 0.0; win.st[1].v3[lane] = 0.0; }
             win.ok[lane] = okb;
+            win_has1 = __any_sync(0xffffffffu, win.st[1].row[lane] != L.st[1].n);
             {   // prefix sums of the b's numbers of states
                 const int ns = hbs == 2 ? 3 : hbs;
                 int c = ns;
@@ -464,10 +467,22 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 if (c_hi > c_lo) nconf += (unsigned)(nstates_a * nstates_x * (win.cum[c_hi] - win.cum[c_lo]));
             }
             const size_t ldp0 = L.st[0].ldp, ldp1 = L.st[1].ldp;
-            double2 nxt[2];                                              // { W[b][x], E{b,x} } of the NEXT step (software prefetch)
-            nxt[0] = wpx[0][(size_t)win.st[0].row[t_lo] * ldp0];
-            nxt[1] = wpx[1][(size_t)win.st[1].row[t_lo] * ldp1];
             unsigned slowmask = 0;
+            // The steps of the segment, specialised at compile time on what the segment cannot contain (all warp-uniform):
+            //   XT   0: the tile has x's of both studies;  1: no lane's x is in study 1;  2: none is in study 0
+            //        -- a study without x has E = 0 for every mask with x: its loads, its chain and two thirds of the products go;
+            //   CH0 / CH1: study s can have a non-zero E{a,b,x} here (a in the study, some b of the window, some x of the tile);
+            //        without it the bordered step -> rsqrt -> exp chain of the study goes.
+            // With the internal SNP order (union SNPs sorted by type: both studies, study 0 only, study 1 only) a < b < x are in
+            // type order, windows and tiles are mostly of one type, and only the triples of three shared SNPs -- 30 % on the
+            // synthetic loci -- need everything.  The generic version (0, true, true) is correct for any segment.
+            auto run_steps = [&](auto xt_, auto ch0_, auto ch1_) {
+            constexpr int XT = decltype(xt_)::value;
+            constexpr bool USE[2] = {XT != 2, XT != 1};                  // study s has x's in this tile
+            constexpr bool CH[2] = {HAS_A && decltype(ch0_)::value && USE[0], HAS_A && decltype(ch1_)::value && USE[1]};
+            double2 nxt[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};   // { W[b][x], E{b,x} } of the NEXT step (software prefetch)
+            if (USE[0]) nxt[0] = wpx[0][(size_t)win.st[0].row[t_lo] * ldp0];
+            if (USE[1]) nxt[1] = wpx[1][(size_t)win.st[1].row[t_lo] * ldp1];
             for (int t = t_lo; t < t_hi; t++) {
                 const bool active = t >= tA && t < tB;
                 double v[2][8];
@@ -478,35 +493,39 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 // row / column of the WP table): the arithmetic stays finite and the zero base E{a,b} or the final select
                 // switch the expansion off.
                 // (written stage by stage over both studies, see xexp_pair)
-                double Wbx[2], e6[2], e7[2] = {0.0, 0.0};
+                double Wbx[2] = {0.0, 0.0}, e6[2] = {0.0, 0.0}, e7[2] = {0.0, 0.0};
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
+                    if (!USE[s]) continue;
                     Wbx[s] = nxt[s].x;
                     e6[s] = nxt[s].y;                                    // E{b,x} from the pair table (0 when b or x is absent)
                     nxt[s] = wpx[s][(size_t)win.st[s].row[t + 1] * (s ? ldp1 : ldp0)];
                 }
-                if (HAS_A) {
-                    double tt[2], s7[2], r7[2], y0[2], ee[2], rs[2], uu[2], arg[2], em[2];
-                    int en[2];
+                if (CH[0] || CH[1]) {
+                    double tt[2], s7[2], r7[2], y0[2], ee[2], rs[2], uu[2], arg[2] = {0.0, 0.0}, em[2] = {0.0, 0.0};
+                    int en[2] = {0, 0};
 #pragma unroll
-                    for (int s = 0; s < 2; s++) tt[s] = fma(-win.st[s].Wab[t], px[s], Wbx[s]);
+                    for (int s = 0; s < 2; s++) if (CH[s]) tt[s] = fma(-win.st[s].Wab[t], px[s], Wbx[s]);
 #pragma unroll
-                    for (int s = 0; s < 2; s++) s7[s] = fma(-tt[s] * tt[s], win.st[s].inv22[t], cx[s]);
+                    for (int s = 0; s < 2; s++) if (CH[s]) s7[s] = fma(-tt[s] * tt[s], win.st[s].inv22[t], cx[s]);
 #pragma unroll
-                    for (int s = 0; s < 2; s++) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[s]) : "d"(s7[s]));
+                    for (int s = 0; s < 2; s++) if (CH[s]) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[s]) : "d"(s7[s]));
 #pragma unroll
-                    for (int s = 0; s < 2; s++) r7[s] = fma(-tt[s], win.st[s].c2[t], rx[s]);       // sqrt(d/2) x the residual
+                    for (int s = 0; s < 2; s++) if (CH[s]) r7[s] = fma(-tt[s], win.st[s].c2[t], rx[s]);       // sqrt(d/2) x the residual
 #pragma unroll
-                    for (int s = 0; s < 2; s++) ee[s] = fma(s7[s], -(y0[s] * y0[s]), 1.0);        // rsqrt_fast, both studies
+                    for (int s = 0; s < 2; s++) if (CH[s]) ee[s] = fma(s7[s], -(y0[s] * y0[s]), 1.0);        // rsqrt_fast, both studies
 #pragma unroll
-                    for (int s = 0; s < 2; s++) rs[s] = fma(fma(ee[s], 0.375, 0.5), y0[s] * ee[s], y0[s]);
+                    for (int s = 0; s < 2; s++) if (CH[s]) rs[s] = fma(fma(ee[s], 0.375, 0.5), y0[s] * ee[s], y0[s]);
 #pragma unroll
-                    for (int s = 0; s < 2; s++) uu[s] = r7[s] * rs[s];
+                    for (int s = 0; s < 2; s++) if (CH[s]) uu[s] = r7[s] * rs[s];
 #pragma unroll
-                    for (int s = 0; s < 2; s++) arg[s] = uu[s] * uu[s];
-                    xexp_pair(arg, em, en);
+                    for (int s = 0; s < 2; s++) if (CH[s]) arg[s] = uu[s] * uu[s];
+                    if (CH[0] && CH[1]) xexp_pair(arg, em, en);
+                    else if (CH[0]) xexp(arg[0], em[0], en[0]);
+                    else xexp(arg[1], em[1], en[1]);
 #pragma unroll
                     for (int s = 0; s < 2; s++) {
+                        if (!CH[s]) continue;
                         en[s] = min(en[s], 1000);
                         const double ex = __hiloint2double(__double2hiint(em[s]) + (en[s] << 20), __double2loint(em[s]));
                         const double e = win.st[s].v3[t] * (ex * rs[s]);                            // v3 = 0 when a or b is absent
@@ -518,7 +537,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     const WinStudy& w = win.st[s];
-                    emax = max(emax, (unsigned)__double2hiint(e6[s]));
+                    if (USE[s]) emax = max(emax, (unsigned)__double2hiint(e6[s]));
                     v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
                     v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6[s]; v[s][7] = e7[s];
                 }
@@ -529,6 +548,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                     const bool on = active && ok;
 #pragma unroll
                     for (int s = 0; s < 2; s++) {
+                        if (!USE[s]) continue;
                         v[s][4] = on ? v[s][4] : 0.0; v[s][5] = on ? v[s][5] : 0.0;
                         v[s][6] = on ? v[s][6] : 0.0; v[s][7] = on ? v[s][7] : 0.0;
                     }
@@ -546,13 +566,16 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                         for (int ta = 0; ta < (HAS_A ? 3 : 1); ta++) {
                             const int m0 = (HAS_A && in0(ta) ? 1 : 0) | (in0(tb) ? 2 : 0) | (in0(tx) ? 4 : 0);
                             const int m1 = (HAS_A && in1(ta) ? 1 : 0) | (in1(tb) ? 2 : 0) | (in1(tx) ? 4 : 0);
+                            // (an expansion whose x state needs a study the tile does not have, or an E{a,b,x} that cannot exist here)
+                            if ((in0(tx) && !USE[0]) || (in1(tx) && !USE[1])) continue;
+                            if (HAS_A && ((m0 == 7 && !CH[0]) || (m1 == 7 && !CH[1]))) continue;
                             const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
                             GX[tx][ac - (tx == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GX[tx][ac - (tx == 2 ? 1 : 0)]);
                             GB[tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GB[tb][ac - (tb == 2 ? 1 : 0)]);
                             if (HAS_A) GA[ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GA[ta][ac - (ta == 2 ? 1 : 0)]);
                         }
-                accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
-                accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
+                if (HAS_A ? CH[0] : USE[0]) accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
+                if (HAS_A ? CH[1] : USE[1]) accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
                 {   // b cells: staged lane by lane; the rows are summed every EXH_STG steps
                     double q[5];
                     cells_of(GB, q);
@@ -561,6 +584,16 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                     if (++slot == EXH_STG) { flush_stage(t + 1 - EXH_STG, EXH_STG); slot = 0; }
                 }
             }  // b window
+            };  // run_steps
+            {
+                typedef std::integral_constant<int, 0> X0; typedef std::integral_constant<int, 1> X1_; typedef std::integral_constant<int, 2> X2_;
+                const bool tile0 = __any_sync(0xffffffffu, hx[0]), tile1 = __any_sync(0xffffffffu, hx[1]);
+                if (!tile1) run_steps(X1_{}, std::true_type{}, std::false_type{});
+                else if (!tile0) {
+                    if (!HAS_A || (ha[1] && win_has1)) run_steps(X2_{}, std::false_type{}, std::true_type{});
+                    else run_steps(X2_{}, std::false_type{}, std::false_type{});
+                } else run_steps(X0{}, std::true_type{}, std::true_type{});
+            }
             if (slot) flush_stage(t_hi - slot, slot);
 
             double accX[5];
