@@ -88,6 +88,12 @@ struct LocusDev {
     double rho;                           // pi'(j, a+1) / pi'(j, a) = p / ((1-p)/2)   (1 when p == 0: postcal.cpp:27)
     int lane_ok;                          // the prior factorises with a finite rho (p < 1): score_lane.cuh may be used
     const uint32_t* exptab[KMAX + 1];     // exptab[k][e] = m0 | m1 << 8 | a << 16 for expansion e of a k-subset
+    // x tiles of the exhaustive kernel (exh_plan.h, ExhTiles): lane l of tile t is x = tile_lo[t] + l, valid when
+    // x >= tile_vmin[t]; tile_of[x] = the tile of x.  Tiles never straddle a boundary between SNP types.
+    const int* tile_lo;
+    const int* tile_vmin;
+    const int* tile_of;
+    int ntiles;
     AccDev acc;
 };
 

@@ -346,6 +346,7 @@ struct pipsort_engine {
     bool lane_smem_set = false;
     ExhScratch exh;
     bool use_reg_kernel = true;
+    ExhCostModel cost_model;           // step costs of the exhaustive kernel from the SNP-type layout (plan + shard boundaries)
     bool capturing = false;
     std::vector<cudaGraphExec_t> graphs;
     uint64_t last_read_count = 0;   // configuration count seen by the last pipsort_read_accumulators
@@ -650,6 +651,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     std::vector<int> u2i(U);
     e->types.resize(U);
     for (int i = 0; i < U; i++) { u2i[e->perm[i]] = i; e->types[i] = type_user[e->perm[i]]; }
+    e->cost_model = exh_cost_model(U, e->types.data());
     for (int s = 0; s < S; s++) {
         e->n_raw[s] = lc->num_snps[s];
         e->loc[s].assign(U, -1);
@@ -671,7 +673,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         size_t est = 64 * 256 + sizeof(LocusDev) + (size_t)(3 + 5 * U + NCOUNTER) * 8 + (size_t)(U + 2) * 8 +
                      ((size_t)NSLOT * 16 * (size_t)std::max((U + 3) & ~3, 4) + NCOUNTER) * 8;
         est += ((size_t)e->sm_count * 12 + 256) * sizeof(int4) + 512;               // chunk descriptors of the exhaustive launch
-        size_t nints = (size_t)5 * U;
+        size_t nints = (size_t)6 * U + 2 * ((size_t)U / 32 + 8);
         for (int s = 0; s < S; s++) {
             const size_t nr = (size_t)lc->num_snps[s], n = e->orig[s].size(), ldw = (n + 3) & ~(size_t)3;
             nints += 2 * n + nr;
@@ -694,7 +696,7 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     // one packed upload of all the small integer arrays:
     //   u2i[U] | snp_map[2U] | loc0[U] | loc1[U] | orig0 | orig1 | raw2loc0 | raw2loc1 | loc2u0 | loc2u1
     int* d_ints = nullptr;
-    size_t orig_off[2], r2l_off[2], l2u_off[2];
+    size_t orig_off[2], r2l_off[2], l2u_off[2], tiles_off = 0;
     std::vector<int> pack;   // function scope: stays alive until the uploads have completed (ev_up below)
     {
         pack.reserve((size_t)5 * U + 2 * (e->orig[0].size() + e->orig[1].size()) + lc->num_snps[0] + lc->num_snps[1]);
@@ -714,9 +716,16 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
             for (int i = 0; i < U; i++) if (e->loc[s][i] >= 0) l2u[e->loc[s][i]] = i;
             pack.insert(pack.end(), l2u.begin(), l2u.end());
         }
+        const ExhTiles& tl = e->cost_model.tiles;                      // x tiles of the exhaustive kernel: lo | vmin | of
+        tiles_off = pack.size();
+        pack.insert(pack.end(), tl.lo.begin(), tl.lo.end());
+        pack.insert(pack.end(), tl.vmin.begin(), tl.vmin.end());
+        pack.insert(pack.end(), tl.of.begin(), tl.of.end());
         if ((rc = dev_alloc(e, &d_ints, pack.size())) || (rc = upload_small(e, d_ints, pack.data(), pack.size() * sizeof(int)))) return rc;
     }
     L.u2i = d_ints;
+    L.ntiles = e->cost_model.tiles.T;
+    L.tile_lo = d_ints + tiles_off; L.tile_vmin = L.tile_lo + L.ntiles; L.tile_of = L.tile_vmin + L.ntiles;
     for (int s = 0; s < S; s++) { L.raw2loc[s] = d_ints + r2l_off[s]; L.loc2u[s] = d_ints + l2u_off[s]; L.n_raw[s] = lc->num_snps[s]; }
     e->d_snp_map = d_ints + U;
     size_t soff = 0, zoff = 0;
@@ -1065,7 +1074,7 @@ int pipsort_run_exhaustive(pipsort_engine* e, int c, uint64_t rank_begin, uint64
     if (jreg >= 0) {
         const bool timed = jdom <= jreg && !e->capturing;
         if ((rc = exhaustive_launch_all(e->L, e->d_L, c, rank_begin, rank_end, e->sm_count, e->stream, &e->launches, &e->exh,
-                                        timed ? e->evk0 : nullptr, timed ? e->evk1 : nullptr)))
+                                        &e->cost_model, timed ? e->evk0 : nullptr, timed ? e->evk1 : nullptr)))
             return fail(PIPSORT_E_CUDA, "exhaustive kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         if (timed) e->evk_valid = true;
     }
@@ -1900,27 +1909,18 @@ static int shard_by_types(const std::vector<int>& types, int c, int parts, uint6
     }
     WorkModel wm(types, std::max(cc, 1));
     // Cost model.  Size classes 2 and 3 run in the register kernel, whose unit of work is a WARP-STEP (a, b, 32-wide
-    // tile of x): its cost hardly depends on how many of the 27 expansions exist (absent ones are multiplications by
-    // zero) nor -- the step being branch-free -- on which studies carry the SNPs.  So a segment of ranks is weighted by its
-    // warp-steps, not by its expanded configurations -- the study-specific SNPs at the end of the internal order have 27x fewer
-    // configurations per subset but cost nearly the same.  Larger classes (generic kernel, one warp per subset)
-    // are weighted per subset.
-    const int ntile = U > 0 ? ((U - 1) >> 5) + 1 : 0;
-    std::vector<double> sp(ntile + 1, 0.0), s0(ntile + 1, 0.0), s1(ntile + 1, 0.0);   // suffix sums over tiles
-    for (int t = ntile - 1; t >= 0; t--) {
-        bool h0 = false, h1 = false;
-        for (int x = t * 32; x < std::min(U, t * 32 + 32); x++) { h0 |= types[x] == 0 || types[x] == 1; h1 |= types[x] == 0 || types[x] == 2; }
-        sp[t] = sp[t + 1] + 1.0; s0[t] = s0[t + 1] + (h0 ? 1.0 : 0.0); s1[t] = s1[t + 1] + (h1 ? 1.0 : 0.0);
-    }
-    auto tcost = [&](int b) -> double {          // warp-steps of (., b, all tiles of x > b)
+    // tile of x); what a step costs depends on which specialised loop its segment runs (ExhCostModel restates the kernel's
+    // dispatch: generic / single-study tile with or without a bordered-step chain).  A segment of ranks is weighted by the
+    // cost of its warp-steps, not by its expanded configurations.  Larger classes (generic kernel, one warp per subset) are
+    // weighted per subset.
+    const ExhCostModel M = exh_cost_model(U, types.data());
+    auto tcost = [&](int J, int a, int b) -> double {          // cost of the warp-steps (a, b, all tiles of x > b)
         if (b + 1 >= U) return 0.0;
-        const int t0 = (b + 1) >> 5;
-        const bool in0 = types[b] == 0 || types[b] == 1, in1 = types[b] == 0 || types[b] == 2;
-        (void)in0; (void)in1;   // the step is branch-free since the studies' chains were interleaved: a tile costs the same
-        return sp[t0];          // whether or not a study can be skipped for it (measured: 8-way split of the 1500-SNP locus)
+        return M.tiles_cost(J, a, b, 1, M.tiles.first_tile(b));
     };
     std::vector<double> w3(U + 1, 0.0);           // w3[a] = sum over b > a
-    for (int a = U - 2; a >= 0; a--) w3[a] = w3[a + 1] + tcost(a + 1);
+    for (int a = U - 2; a >= 0; a--)
+        for (int b = a + 1; b + 1 < U; b++) w3[a] += tcost(3, a, b);
     // segments of consecutive ranks (size class j, smallest element g) with their work estimate
     struct Seg { u64 begin, count; double work; };
     std::vector<Seg> segs;
@@ -1931,7 +1931,7 @@ static int shard_by_types(const std::vector<int>& types, int c, int parts, uint6
             const u64 cnt = binom_host(U - 1 - g, j - 1, nullptr);
             double work;
             if (j == 1) work = 1.0 / 32.0;
-            else if (j == 2) work = 0.8 * tcost(g);
+            else if (j == 2) work = tcost(2, -1, g);
             else if (j == 3) work = w3[g];
             else work = (0.3 * wm.configs_first(j, g) / std::max(1.0, wm.w[g]) + 3.0 * (double)cnt);   // generic kernel: per subset
             segs.push_back({off, cnt, work});

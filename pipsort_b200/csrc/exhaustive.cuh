@@ -58,7 +58,6 @@ inline void exh_unrank(u64 r, int U, int j, int* g) {
 inline bool exh_class_params(ExhParams& P, int U, int j, u64 rb, u64 re) {
     memset(&P, 0, sizeof P);
     P.J = j;
-    P.off = exh_tile_off(U);
     if (U < j || rb >= re) return false;
     const u64 total = exh_binom(U, j);
     P.r_begin = rb; P.r_end = re;
@@ -76,19 +75,33 @@ inline bool exh_class_params(ExhParams& P, int U, int j, u64 rb, u64 re) {
     return true;
 }
 
+// Cost model of a locus (exh_plan.h); PIPSORT_EXH_COSTS="chain,plain,pair,pair1" overrides the measured constants (experiments).
+inline ExhCostModel exh_cost_model(int U, const int* types) {
+    ExhCostModel M(U, types);
+    if (const char* v = getenv("PIPSORT_EXH_COSTS")) {
+        double c[4] = {M.c_chain, M.c_plain, M.c_pair, M.c_pair1};
+        sscanf(v, "%lf,%lf,%lf,%lf", &c[0], &c[1], &c[2], &c[3]);
+        M.c_chain = c[0]; M.c_plain = c[1]; M.c_pair = c[2]; M.c_pair1 = c[3];
+        for (double x : c) M.hash = (M.hash ^ (uint64_t)(x * 4096.0)) * 1099511628211ull;
+    }
+    return M;
+}
+
 // The chunk list for (U, class ranges, number of resident warps): pure arithmetic on U, so it is shared by every engine
 // of the process (a fine-mapping run creates one engine per locus, and loci of equal size are common).
 struct ExhPlanKey {
     int U, c, slots;
     u64 rb, re;
     double forced;
+    u64 types;          // hash of the SNP-type layout (ExhCostModel): the step costs depend on it
     bool operator<(const ExhPlanKey& o) const {
-        return std::tie(U, c, slots, rb, re, forced) < std::tie(o.U, o.c, o.slots, o.rb, o.re, o.forced);
+        return std::tie(U, c, slots, rb, re, forced, types) < std::tie(o.U, o.c, o.slots, o.rb, o.re, o.forced, o.types);
     }
 };
 
 inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const ExhPlanKey& key, bool have3, const ExhParams& p3,
-                                                                       bool have2, int n1_tiles, int tile1_0, int do_null) {
+                                                                       bool have2, int n1_tiles, int tile1_0, int do_null,
+                                                                       const ExhCostModel* M) {
     static std::map<ExhPlanKey, std::shared_ptr<const std::vector<ExhChunkDesc>>> cache;
     static std::mutex mu;
     {
@@ -99,7 +112,7 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
     const int U = key.U;
     ExhCost cs;
     auto plan = std::make_shared<std::vector<ExhChunkDesc>>();
-    const double steps = (have3 ? exh_class_steps(U, 3, p3.a_lo, p3.a_hi) : 0.0) + (have2 ? exh_class_steps(U, 2, 0, 0) : 0.0);
+    const double steps = (have3 ? exh_class_steps(*M, 3, p3.a_lo, p3.a_hi, true) : 0.0) + (have2 ? exh_class_steps(*M, 2, 0, 0, true) : 0.0);
     // Granularity (measured on B200, scripts/sweep_chunks.py).  avg = modelled cost per resident warp.
     //   avg <= 3       : chunks of 3 steps -- fewer chunks than warps (a 1/8 shard of a small locus, a c = 2 run);
     //   avg <= 64      : ONE chunk per resident warp, all of the same cost (a static, even deal: the kernel time of a small
@@ -111,8 +124,8 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
         for (int pass = 0; pass < 2 && avg > 3.0 && avg <= 64.0; pass++) {     // set-up costs depend on the cuts: one refinement
             plan->clear();
             double tot = 0.0;
-            if (have3) tot += exh_plan_class(U, 3, p3.a_lo, p3.a_hi, avg, cs, *plan);
-            if (have2) tot += exh_plan_class(U, 2, 0, 0, avg, cs, *plan);
+            if (have3) tot += exh_plan_class(*M, 3, p3.a_lo, p3.a_hi, avg, cs, *plan);
+            if (have2) tot += exh_plan_class(*M, 2, 0, 0, avg, cs, *plan);
             avg = 1.01 * tot / key.slots;
         }
         if (avg <= 3.0) target = 3.0;
@@ -122,8 +135,8 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
     const bool one_round = !(key.forced > 0.0) && target > 3.0 && target <= 64.0 * 1.02;
     for (int tries = 0; tries < 6; tries++) {
         plan->clear();
-        if (have3) exh_plan_class(U, 3, p3.a_lo, p3.a_hi, target, cs, *plan);
-        if (have2) exh_plan_class(U, 2, 0, 0, target, cs, *plan);
+        if (have3) exh_plan_class(*M, 3, p3.a_lo, p3.a_hi, target, cs, *plan);
+        if (have2) exh_plan_class(*M, 2, 0, 0, target, cs, *plan);
         // one chunk per resident warp means AT MOST one: a handful of left-over chunks would cost a second round
         const double avail = (double)key.slots - n1_tiles - do_null;
         if (!one_round || avail < 1.0 || (double)plan->size() <= avail) break;
@@ -142,8 +155,8 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
 // ev0 / ev1 (optional) are recorded immediately around the kernel launch: the host-side planning is NOT part of the
 // kernel's device time.
 inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u64 rank_begin, u64 rank_end, int sm_count,
-                                 cudaStream_t stream, unsigned long long* launches, ExhScratch* sc, cudaEvent_t ev0 = nullptr,
-                                 cudaEvent_t ev1 = nullptr) {
+                                 cudaStream_t stream, unsigned long long* launches, ExhScratch* sc, const ExhCostModel* M,
+                                 cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr) {
     const int U = L.U;
     cudaError_t err;
     if (!sc->d_counter) {
@@ -180,8 +193,8 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         }
         const int occ = std::max(1, sc->occ);
         const int slots = sm_count * occ * EXH_WARPS;
-        const ExhPlanKey key{U, c, slots, rank_begin, rank_end, forced > 0.0 ? forced : 0.0};
-        auto plan = exh_plan_chunks(key, have3, A.p3, have2, n1_tiles, tile1_0, do_null);
+        const ExhPlanKey key{U, c, slots, rank_begin, rank_end, forced > 0.0 ? forced : 0.0, M ? M->hash : 0};
+        auto plan = exh_plan_chunks(key, have3, A.p3, have2, n1_tiles, tile1_0, do_null, M);
         A.n_total = (unsigned)plan->size();
         sc->plan_valid = false;
         if (A.n_total) {
@@ -207,7 +220,8 @@ inline int exhaustive_launch_all(const LocusDev& L, const LocusDev* Lg, int c, u
         if (debug) {
             double st = 0; unsigned mx = 0;
             for (const ExhChunkDesc& d : *plan) { const unsigned n = d.nsteps_kind & 0x0fffffff; st += n; mx = std::max(mx, n); }
-            fprintf(stderr, "[exhaustive] U=%d c=%d slots=%d chunks=%u steps=%.0f longest=%u\n", U, c, slots, A.n_total, st, mx);
+            fprintf(stderr, "[exhaustive] U=%d c=%d slots=%d chunks=%u steps=%.0f longest=%u cost3=%.0f\n", U, c, slots, A.n_total, st, mx,
+                    have3 ? exh_class_steps(*M, 3, A.p3.a_lo, A.p3.a_hi, true) : 0.0);
         }
         A.chunks = sc->d_chunks;
         A.counter = sc->d_counter;

@@ -120,7 +120,6 @@ constexpr __host__ __device__ bool in1(int t) { return t != 0; }
 
 struct ExhParams {
     int J;                 // 2 or 3
-    int off;               // x tiles are aligned to the top of the SNP range: tile j covers x in [32 j - off, 32 j - off + 32)
     u64 r_begin, r_end;    // in-class rank range (lexicographic over internal order)
     int a_lo, a_hi;        // J == 3: range of a that intersects the rank range
     int lo[3], hi[3];      // lexicographic bounds of the rank range: first subset in range, first subset past it
@@ -266,7 +265,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     constexpr unsigned LIM_HI = (1023u + 450u) << 20;      // high word of FAST_LIMIT: e < 2^450  <=>  hi(e) < LIM_HI  (e >= 0)
     const AccDev& acc = L.acc;
     const int U = L.U;
-    const int off = P.off, T1 = (U - 1 + off) >> 5;
+    const int T1 = L.ntiles - 1;
     const double pi0 = L.pi[J][0], pi1 = L.pi[J][1], pi2 = L.pi[J][2], pi3 = HAS_A ? L.pi[J][3] : 0.0;
     const double shd[2] = {sqrt(L.st[0].hd), sqrt(L.st[1].hd)};   // sqrt(d/2): folded into the residuals, so that the exponent is a plain square
     auto wsumX = [&](const double (&g)[3], bool both) -> double {   // prior-weighted cell value
@@ -392,8 +391,9 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
         }
 
         {
-            const int x = xt * 32 + lane - off;
-            const bool xin = x >= 0;                                     // (the top tile ends exactly at U - 1)
+            const int x_lo = L.tile_lo[xt];
+            const int x = x_lo + lane;
+            const bool xin = x >= L.tile_vmin[xt];                       // (the lowest tile of a group of SNPs starts below the group)
             // ---- per-tile lane values of x: masks {x} (4) and {a,x} (5) ----------------------------------
             int hx[2];
             const double2* wpx[2];                                       // column of x in the study's WP table (the zero column when absent)
@@ -460,7 +460,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             int slot = 0;                                                // staged steps
             // steps of this segment: the b's of the window that have an x of this tile beyond them, from t_lo on, as
             // far as the chunk reaches
-            const int t_hi = min(min(nb, xt * 32 + 31 - off - b0), t_lo + remaining);
+            const int t_hi = min(min(nb, x_lo + 31 - b0), t_lo + remaining);
             remaining -= t_hi - t_lo;
             {   // expanded configurations of the lane's subsets in this segment (the reference's mycount)
                 const int c_lo = max(tA, t_lo), c_hi = min(tB, t_hi);
@@ -625,7 +625,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                     b0 = a + 1;
                     new_a = true;
                 }
-                xt = (b0 + 1 + off) >> 5;
+                xt = L.tile_of[b0 + 1];
             }
         }
     }

@@ -111,7 +111,7 @@ def test_world2_gloo_sharded_run_matches_whole_run():
 @pytest.mark.parametrize("parts", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("keep_order", [False, True])
 def test_shard_planner_partitions_and_balances(parts, keep_order):
-    """Bounds are monotone, cover [0,total) and split the kernel's work (warp-steps) evenly."""
+    """Bounds are monotone, cover [0,total) and split the kernel's work (cost-weighted warp-steps) evenly."""
     L = synth.make_locus(40, overlap=0.5, seed=3)
     c = 3
     U = L.U
@@ -119,10 +119,11 @@ def test_shard_planner_partitions_and_balances(parts, keep_order):
     from math import comb
     total = sum(comb(U, j) for j in range(c + 1))
     assert b[0] == 0 and b[-1] == total and all(x <= y for x, y in zip(b, b[1:]))
-    # the register kernel's unit of work is a warp-step (a, b, 32-wide tile of x), whose cost hardly depends on how many
-    # expansions a subset has: shards must hold similar numbers of warp-steps, i.e. (dense tiles) of union subsets
+    # the register kernel's unit of work is a warp-step (a, b, 32-wide tile of x); a step of a tile whose x's are in one
+    # study only costs 0.4-0.7 of a generic one (ExhCostModel, exh_plan.h), so a shard may hold up to ~2.5x its share of subsets
     sizes = [b[i + 1] - b[i] for i in range(parts)]
-    assert max(sizes) <= 1.35 * total / parts + 64
+    assert max(sizes) <= 2.5 * total / parts + 64
+    assert min(sizes) >= 0.3 * total / parts - 64
     if keep_order:                                  # rank order == snp_map order: the shards partition the configurations
         from oracle import oracle as O
         from conftest import synth_as_oracle_locus
