@@ -113,34 +113,35 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
     ExhCost cs;
     auto plan = std::make_shared<std::vector<ExhChunkDesc>>();
     const double steps = (have3 ? exh_class_steps(*M, 3, p3.a_lo, p3.a_hi, true) : 0.0) + (have2 ? exh_class_steps(*M, 2, 0, 0, true) : 0.0);
-    // Granularity (measured on B200, scripts/sweep_chunks.py).  avg = modelled cost per resident warp.
-    //   avg <= 3       : chunks of 3 steps -- fewer chunks than warps (a 1/8 shard of a small locus, a c = 2 run);
-    //   avg <= 64      : ONE chunk per resident warp, all of the same cost (a static, even deal: the kernel time of a small
-    //                    locus is the time of its longest chunk);
-    //   beyond         : ~avg / 32 (at most 12) chunks per resident warp, balanced by the work queue.
+    // Granularity (measured on B200, scripts/sweep_chunks.py, scripts/trace_chunks.py).  avg = modelled cost per resident
+    // warp, set-up work included (a chunk costs ~3 generic steps before its first step: measured 5.5 us against 1.3 us).
+    //   avg <= 64 : ONE chunk per resident warp, all of the same cost -- a static, even deal: the kernel time of a small locus
+    //               (or of a 1/8 shard of one: 1-3 steps per warp) is the time of its longest chunk, and a second chunk per
+    //               warp would pay the set-up again;
+    //   beyond    : ~avg / 32 (at most 12) chunks per resident warp, balanced by the work queue.
+    const double setup = cs.chunk + cs.win + cs.seg + cs.a;
     double target = key.forced;
     if (!(target > 0.0)) {
-        double avg = 1.15 * steps / key.slots;
-        for (int pass = 0; pass < 2 && avg > 3.0 && avg <= 64.0; pass++) {     // set-up costs depend on the cuts: one refinement
+        double avg = 1.15 * steps / key.slots + setup;
+        for (int pass = 0; pass < 2 && avg <= 64.0; pass++) {     // set-up costs depend on the cuts: one refinement
             plan->clear();
             double tot = 0.0;
             if (have3) tot += exh_plan_class(*M, 3, p3.a_lo, p3.a_hi, avg, cs, *plan);
             if (have2) tot += exh_plan_class(*M, 2, 0, 0, avg, cs, *plan);
-            avg = 1.01 * tot / key.slots;
+            avg = std::max(1.01 * tot / key.slots, setup + 1.0);
         }
-        if (avg <= 3.0) target = 3.0;
-        else if (avg <= 64.0) target = avg;
+        if (avg <= 64.0) target = avg;
         else target = avg / std::min(12.0, std::floor(avg / 32.0));
     }
-    const bool one_round = !(key.forced > 0.0) && target > 3.0 && target <= 64.0 * 1.02;
-    for (int tries = 0; tries < 6; tries++) {
+    const bool one_round = !(key.forced > 0.0) && target <= 64.0 * 1.02;
+    for (int tries = 0; tries < 8; tries++) {
         plan->clear();
         if (have3) exh_plan_class(*M, 3, p3.a_lo, p3.a_hi, target, cs, *plan);
         if (have2) exh_plan_class(*M, 2, 0, 0, target, cs, *plan);
         // one chunk per resident warp means AT MOST one: a handful of left-over chunks would cost a second round
         const double avail = (double)key.slots - n1_tiles - do_null;
         if (!one_round || avail < 1.0 || (double)plan->size() <= avail) break;
-        target *= 1.005 * std::max(1.0, (double)plan->size() / avail);
+        target = std::max(target * 1.005 * std::max(1.0, (double)plan->size() / avail), target + 0.25);
     }
     for (int t = 0; t < n1_tiles; t++) plan->push_back(ExhChunkDesc{tile1_0 + t, 0, 0, 1u << 28});
     if (do_null) plan->push_back(ExhChunkDesc{0, 0, 0, 0u});

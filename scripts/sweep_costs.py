@@ -15,10 +15,10 @@ for _ in range(3):
 ks = []
 for _ in range(60):
     e.reset(); e.flush_l2(); e.run_exhaustive(3); ks.append(e.last_kernel_ms())
-print("%%.4f %%.4f" %% (float(np.median(ks)), min(ks)))
+print("%%.4f %%.4f %%.4f" %% (float(np.mean(ks)), float(np.median(ks)), min(ks)))
 ''' % ROOT
-grid = [(c, p) for c in (0.55, 0.65, 0.75, 0.85, 1.0) for p in (0.3, 0.45, 0.6)] + [(1.0, 1.0)]
+grid = [(c, p) for c in (0.3, 0.4, 0.5, 0.6, 0.7) for p in (0.15, 0.25, 0.4)] + [(1.0, 1.0)]
 for c, p in grid:
     env = dict(os.environ, PIPSORT_EXH_COSTS="%g,%g,0.45,0.3" % (c, p))
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
-    print("c_chain %.2f c_plain %.2f  kernel ms (median, min): %s" % (c, p, out.stdout.strip() or out.stderr[-300:]), flush=True)
+    print("c_chain %.2f c_plain %.2f  kernel ms (mean, median, min): %s" % (c, p, out.stdout.strip() or out.stderr[-300:]), flush=True)
