@@ -95,6 +95,31 @@ def test_forced_plan_shapes(chunk, c):
                 assert_results_match(rs, ws)
 
 
+@pytest.mark.parametrize("overlap", [1.0, 0.0, 0.9, 0.3])
+@pytest.mark.parametrize("chunk", [None, 7])
+def test_type_layouts(overlap, chunk):
+    """The step loops are specialised on what a (window, tile) segment cannot contain, and the x tiles end at the boundaries
+    between SNP types (exh_plan.h, ExhTiles): loci whose type groups are missing (all SNPs shared / none shared), smaller
+    than a tile (45 SNPs per study at 90 % overlap: groups of 40 + 5 + 5; at 30 %: 14 + 31 + 31) -- whole runs in both SNP
+    orders and the sum over the work-weighted shards, size classes 2 and 3, against the oracle."""
+    SL = synth_locus(45, overlap=overlap, seed=5 + int(10 * overlap), sharing_param=0.4)
+    for c in (2, 3):
+        whole = oracle_range(("T45", overlap), SL, c)
+        with exh_plan_env(chunk):
+            for keep in (False, True):
+                with engine_for(SL, c, keep_order=keep) as e:
+                    r = e.compute_total_likelihood(c)
+                    assert r.n_configs == whole.n_eval
+                    assert_results_match(r, whole)
+                    b = e.shard_ranks(c, 5)
+                    e.reset()
+                    for i in range(5):
+                        e.run_exhaustive(c, b[i], b[i + 1])
+                    rs = e.read()
+                    assert rs.n_configs == whole.n_eval
+                    assert_results_match(rs, whole)
+
+
 @pytest.mark.parametrize("forced", [None, 1400, 40])
 def test_b1500c3_rank_ranges_against_oracle(forced):
     """The saturating locus of the roofline claim (1500 SNPs/study, U = 1800, c = 3; 1.2e10 configurations): rank ranges
