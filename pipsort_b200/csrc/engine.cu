@@ -30,6 +30,7 @@
 using namespace pipsort;
 
 #define PIPSORT_INTERNAL_NO_UPLOAD_WAIT 0x80000000u   /* not part of the public flag set */
+#define PIPSORT_INTERNAL_WITH_PAIRS 0x40000000u       /* build the WP tables of the exhaustive kernel in pipsort_create's own launch */
 
 namespace {
 
@@ -73,6 +74,8 @@ struct PrepStudyArgs {
     double d;
     double *W, *A, *z, *invA, *u, *e1m;
     int* e1n;
+    double2* WP;     // (n + 1) x ldp table { W_ij, E{i,j} } of the exhaustive kernel, or nullptr: built later, on demand
+    int ldp;
 };
 struct PrepLocusArgs { PrepStudyArgs s[2]; };
 
@@ -80,23 +83,43 @@ __global__ void __launch_bounds__(128) prepare_locus_kernel(PrepLocusArgs P) {
     const PrepStudyArgs& S = P.s[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
-    if (j >= S.ldw || i >= S.n) return;
+    if (i > S.n || (i == S.n && !S.WP)) return;
+    if (i == S.n) {                                            // the all-zero row of the WP table
+        if (j < S.ldp) S.WP[(size_t)i * S.ldp + j] = make_double2(0.0, 0.0);
+        return;
+    }
     const int oi = S.orig[i];
     double v = 0.0;
     if (j < S.n) v = S.d * S.sigma[(size_t)oi * S.n_raw + S.orig[j]];
-    S.W[(size_t)i * S.ldw + j] = v;
+    if (j < S.ldw) S.W[(size_t)i * S.ldw + j] = v;
+    if (j != 0 && !S.WP) return;
+    // the per-SNP values of i: stored by thread j == 0; every thread of the row needs them for its table entry (computing them
+    // per thread -- one exp -- costs less than a second launch that reads them back: a 150-SNP locus is 38 us of evaluation)
+    const double a = 1.0 + S.d * S.sigma[(size_t)oi * S.n_raw + oi];
+    const double zi = S.z_raw[oi];
+    const double invA = 1.0 / a, u = zi / a;
+    double m;
+    int e;
+    xexp(0.5 * S.d * (zi * zi / a), m, e);
+    const double e1m = m / sqrt(a);
     if (j == 0) {
-        const double a = 1.0 + S.d * S.sigma[(size_t)oi * S.n_raw + oi];
-        const double zi = S.z_raw[oi];
         S.A[i] = a;
         S.z[i] = zi;
-        S.invA[i] = 1.0 / a;
-        S.u[i] = zi / a;
-        double m;
-        int e;
-        xexp(0.5 * S.d * (zi * zi / a), m, e);
-        S.e1m[i] = m / sqrt(a);
+        S.invA[i] = invA;
+        S.u[i] = u;
+        S.e1m[i] = e1m;
         S.e1n[i] = e;
+    }
+    if (S.WP && j < S.ldp) {
+        double2 w = make_double2(0.0, 0.0);                    // columns >= n: the absent SNP
+        if (j < S.n) {
+            w.x = v;
+            if (j != i) {
+                const int oj = S.orig[j];
+                w.y = pair_entry(0.5 * S.d, e1m, e, invA, u, v, 1.0 + S.d * S.sigma[(size_t)oj * S.n_raw + oj], S.z_raw[oj]);
+            }
+        }
+        S.WP[(size_t)i * S.ldp + j] = w;
     }
 }
 
@@ -778,9 +801,14 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
         if ((rc = dev_alloc(e, &A, n)) || (rc = dev_alloc(e, &z, n)) || (rc = dev_alloc(e, &invA, n)) ||
             (rc = dev_alloc(e, &u, n)) || (rc = dev_alloc(e, &e1m, n)) || (rc = dev_alloc(e, &e1n, n)))
             return rc;
-        prep_args.s[s] = PrepStudyArgs{d_sigma, d_zraw, d_orig, n_raw, n, ldw, d, W, A, z, invA, u, e1m, e1n};
+        double2* WP = nullptr;
+        const int ldp = (n + 2) & ~1;
+        if ((flags & PIPSORT_INTERNAL_WITH_PAIRS) && !(flags & PIPSORT_GENERIC_ONLY) && lc->max_causal >= 2)
+            if ((rc = dev_alloc(e, &WP, (size_t)(n + 1) * ldp))) return rc;
+        prep_args.s[s] = PrepStudyArgs{d_sigma, d_zraw, d_orig, n_raw, n, ldw, d, W, A, z, invA, u, e1m, e1n, WP, ldp};
         StudyDev& st = L.st[s];
         st.W = W; st.A = A; st.z = z; st.invA = invA; st.u = u; st.e1m = e1m; st.e1n = e1n;
+        st.WP = WP; st.ldp = ldp;
         st.n = n; st.ldw = ldw; st.hd = 0.5 * d;
         L.loc[s] = d_loc;
         // exponent range: f_s(C) <= d/2 |z_C|^2 (A >= I), E_s(C) >= prod (1 + d Sigma_ii)^(-1/2)
@@ -802,7 +830,9 @@ static int create_impl(const pipsort_locus* lc, int device, uint32_t flags, pips
     }
 
     {   // W = d Sigma~ in the internal order + the per-SNP vectors, both studies, one launch
-        const int nmax = std::max(prep_args.s[0].n, prep_args.s[1].n), lmax = std::max(prep_args.s[0].ldw, prep_args.s[1].ldw);
+        const bool with_pairs = prep_args.s[0].WP != nullptr;
+        const int nmax = std::max(prep_args.s[0].n, prep_args.s[1].n) + (with_pairs ? 1 : 0);
+        const int lmax = std::max(std::max(prep_args.s[0].ldw, prep_args.s[1].ldw), with_pairs ? std::max(prep_args.s[0].ldp, prep_args.s[1].ldp) : 0);
         if (nmax > 0) {
             dim3 grid((lmax + 127) / 128, nmax, 2);
             prepare_locus_kernel<<<grid, 128, 0, e->stream>>>(prep_args);
@@ -1597,7 +1627,7 @@ int pipsort_posterior_exhaustive(const pipsort_locus* locus, int device, uint32_
     const auto t0 = now();
     pipsort_engine* e = nullptr;
     // the caller's buffers stay valid until this function returns: no need to wait for the uploads inside create
-    int rc = pipsort_create(locus, device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT, &e);
+    int rc = pipsort_create(locus, device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT | (c >= 2 ? PIPSORT_INTERNAL_WITH_PAIRS : 0u), &e);
     if (rc) return rc;
     const auto t1 = now();
     uint64_t total = 0;
@@ -1644,7 +1674,7 @@ static int batch_worker(const pipsort_locus* loci, int32_t n_loci, int first, in
         if (inflight[slot]) rc = finish(slot);
         if (rc) break;
         pipsort_engine* e = nullptr;
-        rc = pipsort_create(&loci[i], device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT, &e);
+        rc = pipsort_create(&loci[i], device, flags | PIPSORT_INTERNAL_NO_UPLOAD_WAIT | (c >= 2 ? PIPSORT_INTERNAL_WITH_PAIRS : 0u), &e);
         if (rc) break;
         inflight[slot] = e;
         idx_of[slot] = i;

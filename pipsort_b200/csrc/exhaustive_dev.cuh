@@ -97,22 +97,22 @@ __device__ __forceinline__ double extend_fast(double base, double hd, double r, 
 // per `a` (U times): n^2 exponentials here replace n^3/3 there.  Values outside the fast range (or a lost positive
 // definiteness) are stored as +inf: the kernel then sends the subset down its mantissa/exponent path, which also
 // raises the error flag where the reference would stop.
-__device__ __forceinline__ double pair_table_entry(const StudyDev& S, int i, int j) {
-    double v = 0.0;
-    if (j < S.n && j != i) {
-        const double inf = __longlong_as_double(0x7ff0000000000000ll);
-        const int n = S.e1n[i];
-        const double W = S.W[(size_t)i * S.ldw + j];
-        const double s = fma(-W * W, S.invA[i], S.A[j]);
-        const double r = fma(-W, S.u[i], S.z[j]);
-        v = inf;
-        if (n < 440 && s > 0.25) {
-            int bad = 0;
-            v = extend_fast(scale2(S.e1m[i], n), S.hd, r, s, bad);
-            if (!(v < FAST_LIMIT)) v = inf;
-        }
+// (from the values themselves: the preparation kernel builds the table in the same launch that computes them)
+__device__ __forceinline__ double pair_entry(double hd, double e1m_i, int e1n_i, double invA_i, double u_i, double W, double A_j, double z_j) {
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const double s = fma(-W * W, invA_i, A_j);
+    const double r = fma(-W, u_i, z_j);
+    double v = inf;
+    if (e1n_i < 440 && s > 0.25) {
+        int bad = 0;
+        v = extend_fast(scale2(e1m_i, e1n_i), hd, r, s, bad);
+        if (!(v < FAST_LIMIT)) v = inf;
     }
     return v;
+}
+__device__ __forceinline__ double pair_table_entry(const StudyDev& S, int i, int j) {
+    if (!(j < S.n && j != i)) return 0.0;
+    return pair_entry(S.hd, S.e1m[i], S.e1n[i], S.invA[i], S.u[i], S.W[(size_t)i * S.ldw + j], S.A[j], S.z[j]);
 }
 
 constexpr __host__ __device__ bool in0(int t) { return t != 1; }   // state 0: study 0 only, 1: study 1 only, 2: both

@@ -5,7 +5,7 @@ import pipsort_b200 as P
 from pipsort_b200 import synth
 L = synth.make_locus(150)
 sig = torch.from_numpy(np.concatenate([s.ravel() for s in L.sigma])).pin_memory(); z = torch.from_numpy(np.concatenate(L.z)).pin_memory()
-nb = 160
+nb = int(sys.argv[1]) if len(sys.argv) > 1 else 160
 loci = []
 for i in range(nb):
     sg = sig.clone().pin_memory(); zz = z.clone().pin_memory()
