@@ -1,7 +1,7 @@
 #!/bin/bash
 # evidence for profiles/: plain bench line, launch list, ncu --set full captures of the dominant kernels (current build)
 mkdir -p gpurun_out
-tag=${1:-r2_final}
+tag=${1:-r2c}
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/${tag}_bench_reference.json 2> /dev/null; echo "ref rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_B150c3.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-sat --no-side > /dev/null 2>&1; echo "launch list rc=$?"
