@@ -598,8 +598,9 @@ def main():
                     f"({roof['flop_per_launch']:.4g} flop, {roof['flop_per_config']:.1f}/configuration, SURVEY.md 8d) per launch / its "
                     f"CUDA-event duration ({main_m['kernel_ms']:.4f} ms); peak = DFMA micro-benchmark measured in this run "
                     "(MEASURED_PEAKS.json has no FP64 figure; nominal 37 TFLOP/s). The kernel shares Cholesky work between the "
-                    "expansions of a union subset, so it executes fewer flops than the algorithmic count: frac can exceed 1 on "
-                    "saturating loci; executed FP64 pipe utilisation is in profiles/.")
+                    "expansions of a union subset and skips, at compile time, the expansions a segment of SNPs of one study cannot "
+                    "have, so it executes ~5x fewer flops than the algorithmic count: frac exceeds 1 on saturating loci; the "
+                    "executed FP64 pipe utilisation (ncu) is in profiles/.")
     side = {}
     if args.workload == "B150c3" and not args.no_sat:
         Ls = synth.make_locus(1500, overlap=0.8)
