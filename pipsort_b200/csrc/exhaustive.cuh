@@ -143,6 +143,22 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
         if (!one_round || avail < 1.0 || (double)plan->size() <= avail) break;
         target = std::max(target * 1.005 * std::max(1.0, (double)plan->size() / avail), target + 0.25);
     }
+    if (one_round && plan->size() > 16) {
+        // One chunk per resident warp: what a warp-step costs also depends on what the other warps of its SM are doing (three
+        // warps share an FP64 pipe), and consecutive chunks are of the same kind -- the SMs that got the chunks among the
+        // triples of three shared SNPs finished last (24 us of stepping against 16 for the median warp).  Deal the chunks out
+        // with a stride, so that every CTA and every SM holds a mix.
+        static const bool keep = getenv("PIPSORT_EXH_NO_SHUFFLE") != nullptr;
+        if (!keep) {
+            const size_t n = plan->size();
+            size_t stride = (size_t)(0.6180339887 * (double)n) | 1;
+            auto gcd = [](size_t a, size_t b) { while (b) { const size_t t = a % b; a = b; b = t; } return a; };
+            while (gcd(stride, n) != 1) stride += 2;
+            std::vector<ExhChunkDesc> mixed(n);
+            for (size_t i = 0; i < n; i++) mixed[i] = (*plan)[(i * stride) % n];
+            plan->swap(mixed);
+        }
+    }
     for (int t = 0; t < n1_tiles; t++) plan->push_back(ExhChunkDesc{tile1_0 + t, 0, 0, 1u << 28});
     if (do_null) plan->push_back(ExhChunkDesc{0, 0, 0, 0u});
     std::lock_guard<std::mutex> g(mu);

@@ -7,21 +7,28 @@
 //     x is the LANE's SNP (a 32-wide tile): LD rows a and b are read coalesced, everything that depends on
 //     (a), (a,b) or (a,x) only is computed once per item / window / tile and reused;
 //   * per study the kernel needs E_s(C) = exp(f_s(C)) for the 8 sub-masks of {a,b,x}; 6 of them are loop
-//     invariant, the other two ({b,x} and {a,b,x}) cost one bordered Cholesky step + rsqrt + exp each;
-//   * the <= 27 expansions (postcal.cpp:903-958) are products E_0[m0] E_1[m1], summed per (SNP, state) cell.
+//     invariant, E{b,x} comes with W[b][x] from the interleaved table WP (one 16-byte load per study and step) and
+//     E{a,b,x} costs one bordered Cholesky step + rsqrt + exp;
+//   * the <= 27 expansions (postcal.cpp:903-958) are products E_0[m0] E_1[m1], summed per (SNP, state) cell: the cells of
+//     x and of a accumulate UNWEIGHTED over the steps of the tile / of a (the prior weights are applied once at the end),
+//     the cells of b get theirs per step and are summed over the lanes through a shared-memory staging area;
+//   * the step loop exists in versions specialised on what a (window, tile) segment cannot contain (no x of a study: its
+//     loads, chain and two thirds of the products are not compiled in); the x tiles end at the boundaries between SNP
+//     types, so most segments run a specialised version (run_steps, ExhTiles in exh_plan.h).
 //
 // Two numeric regimes (DESIGN.md "range"):
 //   FAST  every E_s(mask) of the triple is below 2^450: all E's are ordinary doubles, every cell is a plain
 //         double sum, accumulators are plain doubles in lane registers (x cells per tile, a cells per item) or
-//         in the per-warp shared-memory window (b cells, after a shuffle reduction).  No exponent bookkeeping.
-//   SLOW  otherwise (a very strongly associated SNP is involved): the lane re-evaluates the triple with
-//         mantissa/exponent arithmetic, sums each cell relative to its structurally largest term and adds
-//         the results straight to the binned store.  Per-lane, divergent, rare.
+//         in the per-warp shared-memory window (b cells).  No exponent bookkeeping.
+//   SLOW  otherwise (a very strongly associated SNP is involved): the lane notes the step in a mask and, after the
+//         segment's steps, re-evaluates the triple with mantissa/exponent arithmetic, sums each cell relative to its
+//         structurally largest term and adds the results straight to the binned store.  Per-lane, divergent, rare.
 // Both regimes leave the SM as native fp64 atomic adds into the exponent-binned accumulator store (common.cuh).
 //
 // Work decomposition (exh_plan.h): the warp-steps of a size class form one fixed sequence (a, then 32-wide windows of b,
 // then 32-wide tiles of x, then the b's of the window); a CHUNK is a contiguous run of it, handed out by an atomic counter.
-// The union-subset rank range [r_begin, r_end) of the C-ABI is honoured by a lexicographic predicate per lane.
+// The union-subset rank range [r_begin, r_end) of the C-ABI is honoured per lane: for fixed a and x the admissible b's are an
+// interval, computed once per segment from the lexicographic bounds.
 #pragma once
 #include <type_traits>
 
