@@ -257,7 +257,8 @@ int pipsort_shard_ranks_for_map(const int32_t* snp_map, int32_t union_count, int
 
 /* Stream the engine works on (cudaStream_t as void*), and a blocking sync on it.  pipsort_set_stream
  * makes the engine issue all further work on a caller-owned stream (e.g. the one a NCCL all-reduce of
- * pipsort_accumulator_buffer is enqueued on); NULL restores the engine's own stream.                */
+ * pipsort_accumulator_buffer is enqueued on); NULL restores the engine's own stream.  The DEFAULT stream is
+ * named by cudaStreamLegacy ((void*)1), not by NULL.                                                 */
 void* pipsort_stream(pipsort_engine* e);
 int pipsort_set_stream(pipsort_engine* e, void* cuda_stream);
 int pipsort_sync(pipsort_engine* e);

@@ -31,11 +31,21 @@ def world_and_rank(group=None):
     return 1, 0
 
 
+CUDA_STREAM_LEGACY = 1     # cudaStreamLegacy: the handle that NAMES the default stream (0 means "the engine's own stream" to set_stream)
+
+
+def _torch_stream_handle():
+    """torch's current CUDA stream as a handle pipsort_set_stream understands.  torch's default stream is handle 0, which the
+    C-ABI reads as "back to the engine's own (non-blocking) stream" -- an engine "bound" that way is not ordered with NCCL at
+    all; the default stream is therefore passed by its explicit name, cudaStreamLegacy."""
+    import torch
+    return torch.cuda.current_stream().cuda_stream or CUDA_STREAM_LEGACY
+
+
 def bind_engine_to_current_stream(engine):
     """Make the engine launch on torch's current CUDA stream: the NCCL all-reduce torch enqueues is then ordered
     after the engine's kernels (and the finalize kernel after the all-reduce) without host synchronisation."""
-    import torch
-    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    engine.set_stream(_torch_stream_handle())
 
 
 def _order_with_torch(engine):
@@ -49,7 +59,7 @@ def _order_with_torch(engine):
         import torch
         if not torch.cuda.is_available():
             return
-        cur = torch.cuda.current_stream().cuda_stream
+        cur = _torch_stream_handle()
     except Exception:
         return
     if hasattr(engine, "stream") and hasattr(engine, "set_stream") and engine.stream() != cur:
