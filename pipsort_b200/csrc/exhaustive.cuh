@@ -111,6 +111,7 @@ inline std::shared_ptr<const std::vector<ExhChunkDesc>> exh_plan_chunks(const Ex
     }
     const int U = key.U;
     ExhCost cs;
+    if (const char* v = getenv("PIPSORT_EXH_SETUP")) sscanf(v, "%lf,%lf,%lf,%lf", &cs.seg, &cs.win, &cs.a, &cs.chunk);   // experiments
     auto plan = std::make_shared<std::vector<ExhChunkDesc>>();
     const double steps = (have3 ? exh_class_steps(*M, 3, p3.a_lo, p3.a_hi, true) : 0.0) + (have2 ? exh_class_steps(*M, 2, 0, 0, true) : 0.0);
     // Granularity (measured on B200, scripts/sweep_chunks.py, scripts/trace_chunks.py).  avg = modelled cost per resident

@@ -17,6 +17,13 @@ for _ in range(60):
     e.reset(); e.flush_l2(); e.run_exhaustive(3); ks.append(e.last_kernel_ms())
 print("%%.4f %%.4f %%.4f" %% (float(np.mean(ks)), float(np.median(ks)), min(ks)))
 ''' % ROOT
+if "--setup" in sys.argv:      # set-up costs per segment / window / a / chunk, in generic warp-steps (PIPSORT_EXH_SETUP)
+    for setup in ("0.6,0.9,0.5,0.8", "0.6,1.2,1.6,2.4", "0.6,1.0,1.0,1.5", "1.0,1.5,2.0,2.4", "0.3,0.5,0.3,0.8", "0.6,2.0,2.5,2.4"):
+        for rep in range(2):
+            env = dict(os.environ, PIPSORT_EXH_SETUP=setup)
+            out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
+            print("seg,win,a,chunk %s  kernel ms (mean, median, min): %s" % (setup, out.stdout.strip() or out.stderr[-300:]), flush=True)
+    sys.exit(0)
 grid = [(c, p) for c in (0.3, 0.4, 0.5, 0.6, 0.7) for p in (0.15, 0.25, 0.4)] + [(1.0, 1.0)]
 for c, p in grid:
     env = dict(os.environ, PIPSORT_EXH_COSTS="%g,%g,0.45,0.3" % (c, p))
