@@ -242,14 +242,25 @@ __device__ __noinline__ void slow_subset(const LocusDev& L, int a, int b, int x)
 // ---------------------------------------------------------------------------------------------------------
 // per-warp shared-memory window: everything that depends on (a, b) or on b alone, for <= 32 values of b
 // ---------------------------------------------------------------------------------------------------------
-struct WinStudy {
-    double Wab[EXH_BW];    // d Sigma[a][b]                      (0 when a or b is absent from the study)
-    double inv22[EXH_BW];  // 1 / Schur(b | a)
-    double c2[EXH_BW];     // sqrt(d/2) residual(b | a) / Schur(b | a)
-    double v2[EXH_BW];     // E{b}   (0 when b is absent from the study)
-    double v3[EXH_BW];     // E{a,b} (0 when a or b is absent)
-    int row[EXH_BW + 1];   // row of b in the study's WP table; the all-zero row n when b is absent or past the window
+struct alignas(16) WinRec {   // one b of one study: what a step reads, as three 16-byte (warp-uniform) loads
+    double Wab;            // d Sigma[a][b]                      (0 when a or b is absent from the study)
+    double inv22;          // 1 / Schur(b | a)
+    double c2;             // sqrt(d/2) residual(b | a) / Schur(b | a)
+    double v3;             // E{a,b} (0 when a or b is absent)
+    double v2;             // E{b}   (0 when b is absent from the study)
+    int row1;              // row of the NEXT b in the study's WP table (the step prefetches it)
+    int ok;                // E{b}, E{a,b} within the fast range in BOTH studies
 };
+struct WinStudy {
+    WinRec rec[EXH_BW];
+    int row[EXH_BW + 4];   // row of b in the study's WP table; the all-zero row n when b is absent or past the window
+};
+__device__ __forceinline__ void win_load(const WinRec& r, double& Wab, double& inv22, double& c2, double& v3, double& v2, int& row1, int& ok) {
+    const double2* p = reinterpret_cast<const double2*>(&r);
+    const double2 q0 = p[0], q1 = p[1], q2 = p[2];
+    Wab = q0.x; inv22 = q0.y; c2 = q1.x; v3 = q1.y; v2 = q2.x;
+    row1 = __double2loint(q2.y); ok = __double2hiint(q2.y);
+}
 struct alignas(16) WarpWin {
     // staging area of the b-cell values: a step writes its five values lane by lane into rows (slot, cell); every EXH_STG
     // steps lane 5 slot + cell sums its row (16 loads of 16 bytes) into `part` -- no shuffles, and one addition per value
@@ -258,8 +269,7 @@ struct alignas(16) WarpWin {
     WinStudy st[2];
     // b-cell accumulators of the window, flushed when the window is left
     double part[EXH_BW][5];
-    int cum[EXH_BW + 1];     // cum[t] = number of states of the b's before step t (prefix sums: configuration count per segment)
-    int ok[EXH_BW];          // E{b}, E{a,b} within the fast range in both studies
+    int cum[EXH_BW + 4];     // cum[t] = number of states of the b's before step t (prefix sums: configuration count per segment)
 };
 
 // One chunk of size class J (2 or 3): `remaining` warp-steps starting at step t_lo of the segment (a, window at b0,
@@ -352,10 +362,11 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             const int b = b0 + lane;
             const bool bv = lane < nb;
             int okb = 1, hbs = 0;
+            WinRec rec[2];
+            int rowv[2];
 #pragma unroll
             for (int s = 0; s < 2; s++) {
                 const StudyDev& S = L.st[s];
-                WinStudy& w = win.st[s];
                 const int lb = bv ? L.loc[s][b] : -1;
                 const bool hb = lb >= 0;
                 hbs += hb;
@@ -376,14 +387,22 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 const double r2 = fma(-Wab, ua[s], zb);
                 const double inv22 = 1.0 / s22;
                 if (HAS_A && ha[s] && hb) bad |= !(s22 > 0.25);
-                w.Wab[lane] = Wab; w.inv22[lane] = inv22; w.c2[lane] = shd[s] * (r2 * inv22);
-                w.v2[lane] = v2; w.v3[lane] = v3;
-                w.row[lane] = hb ? lb : S.n;
-                if (lane == 0) w.row[EXH_BW] = S.n;
+                rec[s].Wab = Wab; rec[s].inv22 = inv22; rec[s].c2 = shd[s] * (r2 * inv22);
+                rec[s].v2 = v2; rec[s].v3 = v3;
+                rowv[s] = hb ? lb : S.n;
             }
-            if (!okb) { win.st[0].v2[lane] = 0.0; win.st[0].v3[lane] = 0.0; win.st[1].v2[lane] = 0.0; win.st[1].v3[lane] = 0.0; }
-            win.ok[lane] = okb;
-            win_has1 = __any_sync(0xffffffffu, win.st[1].row[lane] != L.st[1].n);
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                WinStudy& w = win.st[s];
+                if (!okb) { rec[s].v2 = 0.0; rec[s].v3 = 0.0; }
+                const int nxt_row = __shfl_down_sync(0xffffffffu, rowv[s], 1);
+                rec[s].row1 = lane < EXH_BW - 1 ? nxt_row : L.st[s].n;
+                rec[s].ok = okb;
+                w.rec[lane] = rec[s];
+                w.row[lane] = rowv[s];
+                if (lane < 4) w.row[EXH_BW + lane] = L.st[s].n;
+            }
+            win_has1 = __any_sync(0xffffffffu, rowv[1] != L.st[1].n);
             {   // prefix sums of the b's numbers of states
                 const int ns = hbs == 2 ? 3 : hbs;
                 int c = ns;
@@ -501,24 +520,28 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 // switch the expansion off.
                 // (written stage by stage over both studies, see xexp_pair)
                 double Wbx[2] = {0.0, 0.0}, e6[2] = {0.0, 0.0}, e7[2] = {0.0, 0.0};
+                double wWab[2], wInv22[2], wC2[2], wV3[2], wV2[2];       // the window table's record of this step, both studies
+                int wRow1[2], wOk[2];
+#pragma unroll
+                for (int s = 0; s < 2; s++) win_load(win.st[s].rec[t], wWab[s], wInv22[s], wC2[s], wV3[s], wV2[s], wRow1[s], wOk[s]);
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                     if (!USE[s]) continue;
                     Wbx[s] = nxt[s].x;
                     e6[s] = nxt[s].y;                                    // E{b,x} from the pair table (0 when b or x is absent)
-                    nxt[s] = wpx[s][(size_t)win.st[s].row[t + 1] * (s ? ldp1 : ldp0)];
+                    nxt[s] = wpx[s][(size_t)wRow1[s] * (s ? ldp1 : ldp0)];
                 }
                 if (CH[0] || CH[1]) {
                     double tt[2], s7[2], r7[2], y0[2], ee[2], rs[2], uu[2], arg[2] = {0.0, 0.0}, em[2] = {0.0, 0.0};
                     int en[2] = {0, 0};
 #pragma unroll
-                    for (int s = 0; s < 2; s++) if (CH[s]) tt[s] = fma(-win.st[s].Wab[t], px[s], Wbx[s]);
+                    for (int s = 0; s < 2; s++) if (CH[s]) tt[s] = fma(-wWab[s], px[s], Wbx[s]);
 #pragma unroll
-                    for (int s = 0; s < 2; s++) if (CH[s]) s7[s] = fma(-tt[s] * tt[s], win.st[s].inv22[t], cx[s]);
+                    for (int s = 0; s < 2; s++) if (CH[s]) s7[s] = fma(-tt[s] * tt[s], wInv22[s], cx[s]);
 #pragma unroll
                     for (int s = 0; s < 2; s++) if (CH[s]) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0[s]) : "d"(s7[s]));
 #pragma unroll
-                    for (int s = 0; s < 2; s++) if (CH[s]) r7[s] = fma(-tt[s], win.st[s].c2[t], rx[s]);       // sqrt(d/2) x the residual
+                    for (int s = 0; s < 2; s++) if (CH[s]) r7[s] = fma(-tt[s], wC2[s], rx[s]);                 // sqrt(d/2) x the residual
 #pragma unroll
                     for (int s = 0; s < 2; s++) if (CH[s]) ee[s] = fma(s7[s], -(y0[s] * y0[s]), 1.0);        // rsqrt_fast, both studies
 #pragma unroll
@@ -535,7 +558,7 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                         if (!CH[s]) continue;
                         en[s] = min(en[s], 1000);
                         const double ex = __hiloint2double(__double2hiint(em[s]) + (en[s] << 20), __double2loint(em[s]));
-                        const double e = win.st[s].v3[t] * (ex * rs[s]);                            // v3 = 0 when a or b is absent
+                        const double e = wV3[s] * (ex * rs[s]);                                     // v3 = 0 when a or b is absent
                         e7[s] = hx[s] ? e : 0.0;
                         smin = min(smin, __double2hiint(s7[s]));                  // (signed: negative values fail too; NaN shows up in e)
                         emax = max(emax, (unsigned)__double2hiint(e));
@@ -545,11 +568,11 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 for (int s = 0; s < 2; s++) {
                     const WinStudy& w = win.st[s];
                     if (USE[s]) emax = max(emax, (unsigned)__double2hiint(e6[s]));
-                    v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = w.v2[t]; v[s][3] = w.v3[t];
+                    v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = wV2[s]; v[s][3] = wV3[s];
                     v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6[s]; v[s][7] = e7[s];
                 }
                 // fast path: every E below 2^450 (as unsigned high words: negative or NaN fails), every Schur complement >= 1/4
-                const bool ok = okX && win.ok[t] && emax < LIM_HI && smin >= 0x3fd00000;
+                const bool ok = okX && wOk[0] && emax < LIM_HI && smin >= 0x3fd00000;
                 if (active && !ok) slowmask |= 1u << t;             // rare: re-evaluated after the loop (slow_subset)
                 {                                                   // a lane that is off contributes nothing on the fast path
                     const bool on = active && ok;
