@@ -270,6 +270,8 @@ struct alignas(16) WarpWin {
     // b-cell accumulators of the window, flushed when the window is left
     double part[EXH_BW][5];
     int cum[EXH_BW + 4];     // cum[t] = number of states of the b's before step t (prefix sums: configuration count per segment)
+    // a cells, unweighted (GA[state][a'] per lane): they live as long as a does but are only touched once per tile
+    double ga[9][32];
 };
 
 // One chunk of size class J (2 or 3): `remaining` warp-steps starting at step t_lo of the segment (a, window at b0,
@@ -289,10 +291,20 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
         return both ? fma(g[0], pi1, fma(g[1], pi2, g[2] * pi3)) : fma(g[0], pi0, fma(g[1], pi1, g[2] * pi2));
     };
     auto sumY = [&](const double (&g)[3]) -> double { return g[0] + g[1] + g[2]; };
-    // chunk-lifetime accumulators (lane private, plain doubles): the scalars; a cells live as long as a does
-    // GA[state][a'] = the a cells, UNWEIGHTED: the products of the expansions accumulate straight into them step after step;
-    // the prior weights are applied when a is left
-    double GA[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+    // chunk-lifetime accumulators (lane private, plain doubles): the scalars.  The a cells GA[state][a'] live as long as a
+    // does, UNWEIGHTED (the prior weights are applied when a is left), in the lane's column of win.ga: they are only touched
+    // once per tile (below)
+    double accT = 0.0, accNC0 = 0.0, accNC1 = 0.0;
+    if (HAS_A) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) win.ga[i][lane] = 0.0;
+    }
+    auto take_ga = [&](double (&g)[3][3]) {      // read the a cells and leave them empty
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) { g[i][q] = win.ga[i * 3 + q][lane]; win.ga[i * 3 + q][lane] = 0.0; }
+    };
     unsigned nconf = 0;
     int bad = 0;
     int ha[2] = {0, 0}, la[2] = {-1, -1};
@@ -307,7 +319,8 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     };
     auto flush_a = [&]() {        // a cells of the a that is being left: five sums over the warp, one atomic each
         if (HAS_A) {
-            double accA[5], mine = 0.0;
+            double GA[3][3], accA[5], mine = 0.0;
+            take_ga(GA);
             cells_of(GA, accA);
 #pragma unroll
             for (int k = 0; k < 5; k++) {
@@ -316,10 +329,6 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
                 if (lane == k) mine = r;
             }
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-                for (int q = 0; q < 3; q++) GA[i][q] = 0.0;
             if (lane < 5) bin_add(acc, lane, a, mine, 0);
         }
     };
@@ -467,7 +476,14 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 tA = max(tA, bmin - b0);
                 tB = min(tB, bmax - b0);
             }
-            double GX[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // the x cells of the tile, unweighted (like GA)
+            // SX[ta][tx][b in both studies?]: the tile's sums over the steps of the 27 products, b's state reduced to its class.
+            // Both the x cells (summed over a's states) and the tile's share of the a cells (summed over x's states) follow
+            // from it at the end of the tile: ONE accumulation per product and step instead of one for x and one for a.
+            double SX[3][3][2];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) { SX[i][q][0] = 0.0; SX[i][q][1] = 0.0; }
             // b cells: `ns` steps starting at step tb are staged; lane 5 slot + cell sums row (slot, cell) over the 32 lanes
             auto flush_stage = [&](int tb, int ns) {
                 __syncwarp();
@@ -585,8 +601,8 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 }
 
                 // ---- cells: G[state][a'] = sum over the expansions with one SNP in that state, a' = number of OTHER SNPs causal
-                // in both studies.  The x cells (GX) and the a cells (GA) go on accumulating over the steps of the tile / of a:
-                // the 27 products are all the arithmetic they cost per step.  The b cells of the step get their prior weights here.
+                // in both studies.  The x and a cells accumulate over the steps of the tile through SX (above): the 27 products are
+                // all the arithmetic they cost per step.  The b cells of the step get their prior weights here.
                 double GB[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
 #pragma unroll
                 for (int tx = 0; tx < 3; tx++)
@@ -600,9 +616,8 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                             if ((in0(tx) && !USE[0]) || (in1(tx) && !USE[1])) continue;
                             if (HAS_A && ((m0 == 7 && !CH[0]) || (m1 == 7 && !CH[1]))) continue;
                             const int ac = (HAS_A && ta == 2 ? 1 : 0) + (tb == 2 ? 1 : 0) + (tx == 2 ? 1 : 0);
-                            GX[tx][ac - (tx == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GX[tx][ac - (tx == 2 ? 1 : 0)]);
+                            SX[ta][tx][tb == 2 ? 1 : 0] = fma(v[0][m0], v[1][m1], SX[ta][tx][tb == 2 ? 1 : 0]);
                             GB[tb][ac - (tb == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GB[tb][ac - (tb == 2 ? 1 : 0)]);
-                            if (HAS_A) GA[ta][ac - (ta == 2 ? 1 : 0)] = fma(v[0][m0], v[1][m1], GA[ta][ac - (ta == 2 ? 1 : 0)]);
                         }
                 if (HAS_A ? CH[0] : USE[0]) accNC1 = fma(pi0, v[0][HAS_A ? 7 : 6], accNC1);
                 if (HAS_A ? CH[1] : USE[1]) accNC0 = fma(pi0, v[1][HAS_A ? 7 : 6], accNC0);
@@ -626,6 +641,23 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
             }
             if (slot) flush_stage(t_hi - slot, slot);
 
+            double GX[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};   // x cells of the tile, a cells of (a, tile): unweighted
+            double GT[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+            for (int ta = 0; ta < (HAS_A ? 3 : 1); ta++)
+#pragma unroll
+                for (int tx = 0; tx < 3; tx++)
+#pragma unroll
+                    for (int cb = 0; cb < 2; cb++) {
+                        GX[tx][cb + (ta == 2 ? 1 : 0)] += SX[ta][tx][cb];
+                        if (HAS_A) GT[ta][cb + (tx == 2 ? 1 : 0)] += SX[ta][tx][cb];
+                    }
+            if (HAS_A) {
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++) win.ga[i * 3 + q][lane] += GT[i][q];
+            }
             double accX[5];
             cells_of(GX, accX);
             accT += (accX[X1] + accX[X2]) + accX[X3];   // every expansion is in exactly one x cell: the total, once per tile
@@ -662,8 +694,12 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
     // ---- end of the chunk: b window, a cells, scalars ---------------------------------------------------------------
     flush_window();
     {
-        double r[8], accA[5];
-        cells_of(GA, accA);
+        double r[8], accA[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (HAS_A) {
+            double GA[3][3];
+            take_ga(GA);
+            cells_of(GA, accA);
+        }
 #pragma unroll
         for (int k = 0; k < 5; k++) r[k] = accA[k];
         r[5] = accT; r[6] = accNC0; r[7] = accNC1;
