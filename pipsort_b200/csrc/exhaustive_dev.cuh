@@ -582,7 +582,6 @@ __device__ __forceinline__ void exh_chunk(const LocusDev& L, const ExhParams& P,
                 }
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
-                    const WinStudy& w = win.st[s];
                     if (USE[s]) emax = max(emax, (unsigned)__double2hiint(e6[s]));
                     v[s][0] = 1.0; v[s][1] = v1[s]; v[s][2] = wV2[s]; v[s][3] = wV3[s];
                     v[s][4] = v4[s]; v[s][5] = v5[s]; v[s][6] = e6[s]; v[s][7] = e7[s];
